@@ -1,0 +1,98 @@
+"""ctypes binding of libgsdr_b200.so — the C ABI declared in include/gsdr/{fir,adjust_frequency,b200}.h.
+
+There is deliberately no fallback: if the shared library is missing or a symbol cannot be resolved, importing
+this module raises.  (Use `python -m gsdr_b200.build` or `__graft_entry__.build()` to compile it.)
+"""
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+
+LIB_PATH = Path(__file__).resolve().parent / "csrc" / "libgsdr_b200.so"
+
+c_size_t = C.c_size_t
+c_void_p = C.c_void_p
+c_int32 = C.c_int32
+c_float = C.c_float
+cudaError_t = C.c_int
+
+
+class Shard(C.Structure):
+    """gsdrShard of include/gsdr/b200.h."""
+
+    _fields_ = [
+        ("firstOutput", C.c_uint64),
+        ("numOutputs", C.c_uint64),
+        ("firstInput", C.c_uint64),
+        ("numInputs", C.c_uint64),
+        ("firstSampleIndex", C.c_uint64),
+    ]
+
+
+class KernelInfo(C.Structure):
+    """gsdrB200KernelInfo of include/gsdr/b200.h."""
+
+    _fields_ = [
+        ("variant", C.c_int),
+        ("outputsPerThread", C.c_int),
+        ("threadsPerBlock", C.c_int),
+        ("smCount", C.c_int),
+        ("outputsPerBlock", c_size_t),
+        ("sharedBytesPerBlock", c_size_t),
+        ("numBlocks", c_size_t),
+    ]
+
+
+_FIR_ARGS = [c_size_t, c_void_p, c_size_t, c_void_p, c_void_p, c_size_t, c_int32, c_void_p]
+_NCO_ARGS = [c_float, c_float, c_size_t] + _FIR_ARGS
+_BATCH_ARGS = [c_size_t, c_void_p, c_size_t, c_size_t, c_void_p, c_size_t, c_void_p, c_size_t, c_size_t, c_size_t,
+               c_int32, c_void_p]
+
+# name -> (restype, argtypes); every symbol the headers declare is listed here and checked at import.
+SIGNATURES = {
+    # include/gsdr/fir.h
+    "gsdrFirFC": (cudaError_t, _FIR_ARGS),
+    "gsdrFirFF": (cudaError_t, _FIR_ARGS),
+    "gsdrFirCC": (cudaError_t, _FIR_ARGS),
+    "gsdrFirCF": (cudaError_t, _FIR_ARGS),
+    # include/gsdr/adjust_frequency.h
+    "gsdrAdjustFrequencyFirFC": (cudaError_t, _NCO_ARGS),
+    "gsdrAdjustFrequencyFirFCLiteral": (cudaError_t, _NCO_ARGS),
+    "gsdrNcoPhaseStep": (C.c_uint64, [c_float, c_float]),
+    # include/gsdr/b200.h
+    "gsdrFirNumOutputs": (c_size_t, [c_size_t, c_size_t, c_size_t]),
+    "gsdrFirNumInputs": (c_size_t, [c_size_t, c_size_t, c_size_t]),
+    "gsdrFirFCBatched": (cudaError_t, _BATCH_ARGS),
+    "gsdrFirFFBatched": (cudaError_t, _BATCH_ARGS),
+    "gsdrShardPlanTime": (C.c_int, [C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint32,
+                                    C.POINTER(Shard)]),
+    "gsdrShardPlanChannels": (C.c_int, [C.c_uint64, C.c_uint32, C.c_uint32, C.POINTER(C.c_uint64),
+                                        C.POINTER(C.c_uint64)]),
+    "gsdrHostPipelineCreate": (cudaError_t, [c_int32, c_size_t, C.c_int, C.POINTER(c_void_p)]),
+    "gsdrHostPipelineDestroy": (None, [c_void_p]),
+    "gsdrFirFCHost": (cudaError_t, [c_void_p, c_size_t, c_void_p, c_size_t, c_void_p, c_void_p, c_size_t]),
+    "gsdrFirFFHost": (cudaError_t, [c_void_p, c_size_t, c_void_p, c_size_t, c_void_p, c_void_p, c_size_t]),
+    "gsdrAdjustFrequencyFirFCHost": (cudaError_t, [c_void_p, c_float, c_float, c_size_t, c_size_t, c_void_p, c_size_t,
+                                                   c_void_p, c_void_p, c_size_t]),
+    "gsdrFirFCMultiGpuHost": (cudaError_t, [C.POINTER(c_void_p), C.c_int, c_size_t, c_void_p, c_size_t, c_void_p,
+                                            c_void_p, c_size_t]),
+    "gsdrB200DescribeKernel": (C.c_int, [C.c_int, c_size_t, c_size_t, c_size_t, c_int32, C.POINTER(KernelInfo)]),
+    "gsdrB200SetKernelVariant": (C.c_int, [C.c_int]),
+    "gsdrB200NumKernelVariants": (C.c_int, []),
+}
+
+
+def _load() -> C.CDLL:
+    if not LIB_PATH.exists():
+        raise ImportError(
+            f"{LIB_PATH} is missing: the CUDA library has not been built (run `python -m gsdr_b200.build`). "
+            "gsdr_b200 has no CPU fallback.")
+    lib = C.CDLL(str(LIB_PATH))
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the .so does not export a declared symbol
+        fn.restype = res
+        fn.argtypes = args
+    return lib
+
+
+lib = _load()

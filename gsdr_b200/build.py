@@ -1,0 +1,93 @@
+"""In-tree build of libgsdr_b200.so (sm_100a only) and of the test oracle.
+
+The product library is `gsdr_b200/csrc/libgsdr_b200.so`; it links nothing but the CUDA runtime.  The oracle
+(`oracle/libgsdr_oracle.so`) and the compiled reference (`oracle/_ref/libgsdr_ref.so`) are test infrastructure:
+they are built here so they travel to the GPU box with the snapshot, but the product never loads them.
+"""
+from __future__ import annotations
+
+import os
+import shutil
+import subprocess
+import sys
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent.parent
+CSRC = ROOT / "gsdr_b200" / "csrc"
+LIB = CSRC / "libgsdr_b200.so"
+SOURCES = [CSRC / "gsdr_fir.cu", CSRC / "gsdr_host.cu"]
+HEADERS = sorted(CSRC.glob("*.cuh")) + sorted(CSRC.glob("*.h")) + sorted((ROOT / "include" / "gsdr").glob("*.h"))
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a",
+    "-O3", "-lineinfo", "-std=c++17",
+    "-Xcompiler", "-fPIC,-fvisibility=hidden",
+    "-Xptxas", "-v",
+]
+
+
+def _nvcc() -> str:
+    for cand in (os.environ.get("NVCC"), "/usr/local/cuda/bin/nvcc", shutil.which("nvcc")):
+        if cand and Path(cand).exists():
+            return cand
+    raise RuntimeError("nvcc not found; libgsdr_b200.so cannot be built")
+
+
+def _stale(target: Path, deps) -> bool:
+    if not target.exists():
+        return True
+    t = target.stat().st_mtime
+    return any(Path(d).stat().st_mtime > t for d in deps)
+
+
+def build_library(force: bool = False, verbose: bool = False) -> Path:
+    if not force and not _stale(LIB, SOURCES + HEADERS + [Path(__file__)]):
+        return LIB
+    cmd = [_nvcc(), *NVCC_FLAGS, "-shared", "-I", str(ROOT / "include"), "-I", str(CSRC),
+           "-o", str(LIB), *map(str, SOURCES)]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    log = res.stdout + res.stderr
+    (CSRC / "build.log").write_text(" ".join(cmd) + "\n" + log)
+    if res.returncode != 0:
+        sys.stderr.write(log)
+        raise RuntimeError("nvcc failed building libgsdr_b200.so")
+    if verbose:
+        print(log)
+    return LIB
+
+
+def build_tools(force: bool = False) -> Path:
+    """tools/libubench_fp32.so — FP32 FFMA/FFMA2 peak microbenchmark used by bench.py for the roofline."""
+    src = ROOT / "tools" / "ubench_fp32.cu"
+    lib = ROOT / "tools" / "libubench_fp32.so"
+    if force or _stale(lib, [src]):
+        cmd = [_nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-Xcompiler", "-fPIC",
+               "-shared", "-o", str(lib), str(src)]
+        subprocess.run(cmd, check=True, capture_output=True)
+    return lib
+
+
+def build_oracle(force: bool = False) -> Path:
+    odir = ROOT / "oracle"
+    lib = odir / "libgsdr_oracle.so"
+    if force or _stale(lib, [odir / "gsdr_oracle.c", odir / "gsdr_oracle.h", odir / "Makefile"]):
+        subprocess.run(["make", "-C", str(odir), "-B"], check=True, capture_output=True)
+    return lib
+
+
+def build_reference() -> Path | None:
+    """Compiles the reference's own kernels when /root/reference is present (never on the GPU box)."""
+    odir = ROOT / "oracle"
+    lib = odir / "_ref" / "libgsdr_ref.so"
+    ref = Path(os.environ.get("GSDR_REFERENCE_DIR", "/root/reference"))
+    if (ref / "src" / "fir.cu").exists():
+        if _stale(lib, [odir / "build_ref.sh", odir / "ref_adjust_harness.cu"]):
+            subprocess.run(["bash", str(odir / "build_ref.sh")], check=True, capture_output=True)
+    return lib if lib.exists() else None
+
+
+if __name__ == "__main__":
+    print(build_library(force="--force" in sys.argv, verbose=True))
+    print(build_tools())
+    print(build_oracle())
+    print(build_reference())

@@ -1,0 +1,50 @@
+// launch.h — internal host-side launch interface shared by the C-ABI translation units.
+#pragma once
+
+#include <cuComplex.h>
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+namespace gsdr_b200 {
+
+enum FirType : int { kFirFC = 0, kFirFF = 1, kFirCC = 2, kFirCF = 3 };
+enum NcoMode : int { kNcoNone = 0, kNcoExact = 1, kNcoLiteral = 2 };
+
+struct FirCall {
+  FirType type = kFirFC;
+  NcoMode nco = kNcoNone;
+  size_t decimation = 1;
+  const void* taps = nullptr;
+  size_t tapCount = 0;
+  const void* input = nullptr;
+  void* output = nullptr;
+  size_t numOutputs = 0;
+  // batching: numChannels independent filters in one launch; strides in elements (tapStride 0 = shared taps)
+  size_t numChannels = 1;
+  size_t inputStride = 0, outputStride = 0, tapStride = 0;
+  // NCO
+  float sampleRate = 0.0f, frequencyShift = 0.0f;
+  size_t firstSampleIndex = 0;
+};
+
+// Enqueue on `stream` of the CURRENT device (callers switch devices). No sync, no allocation.
+cudaError_t enqueueFir(const FirCall& call, cudaStream_t stream) noexcept;
+
+// Saves the current device, switches to `device`, restores on destruction (ref: the SIMPLE_CUDA_FNC_START/END
+// pair at src/cuComplexOperatorOverloads.cuh:74-93).
+class DeviceScope {
+ public:
+  explicit DeviceScope(int32_t device) noexcept;
+  ~DeviceScope() noexcept;
+  cudaError_t status() const noexcept { return status_; }
+
+ private:
+  int previous_ = -1;
+  bool switched_ = false;
+  cudaError_t status_ = cudaSuccess;
+};
+
+uint64_t ncoPhaseStep(float frequencyShift, float sampleRate) noexcept;
+
+}  // namespace gsdr_b200

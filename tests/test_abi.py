@@ -1,0 +1,85 @@
+"""The C-ABI library loads and exports every symbol include/gsdr/*.h declares (no compute calls: no GPU here)."""
+import ctypes
+import re
+import subprocess
+from pathlib import Path
+
+import pytest
+
+ROOT = Path(__file__).resolve().parent.parent
+INCLUDE = ROOT / "include" / "gsdr"
+
+
+def _declared_symbols():
+    names = set()
+    for h in sorted(INCLUDE.glob("*.h")):
+        text = re.sub(r"/\*.*?\*/", "", h.read_text(), flags=re.S)
+        for m in re.finditer(r"GSDR_PUBLIC\s+[\w\s\*]+?\b(gsdr\w+)\s*\(", text):
+            names.add(m.group(1))
+    return sorted(names)
+
+
+def test_headers_declare_the_reference_fir_entry_points():
+    d = _declared_symbols()
+    for name in ("gsdrFirFC", "gsdrFirFF", "gsdrFirCC", "gsdrFirCF", "gsdrAdjustFrequencyFirFC"):
+        assert name in d
+
+
+def test_library_exports_every_declared_symbol():
+    from gsdr_b200 import _lib
+
+    lib = ctypes.CDLL(str(_lib.LIB_PATH))
+    declared = _declared_symbols()
+    assert len(declared) >= 20
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in include/gsdr but not exported"
+        assert name in _lib.SIGNATURES, f"{name} has no ctypes signature in gsdr_b200/_lib.py"
+
+
+def test_no_undeclared_gsdr_exports():
+    from gsdr_b200 import _lib
+
+    out = subprocess.run(["nm", "-D", "--defined-only", str(_lib.LIB_PATH)], capture_output=True, text=True).stdout
+    exported = {line.split()[-1] for line in out.splitlines() if " T " in line and line.split()[-1].startswith("gsdr")}
+    assert exported == set(_declared_symbols())
+
+
+def test_fir_signature_matches_reference_argument_order():
+    """(decimation, taps, tapCount, input, output, numOutputs, cudaDevice, cudaStream), ref: include/gsdr/fir.h:30-38."""
+    text = (INCLUDE / "fir.h").read_text()
+    m = re.search(r"cudaError_t gsdrFirFC\((.*?)\)", text, flags=re.S)
+    params = [p.strip().split()[-1].lstrip("*") for p in m.group(1).split(",")]
+    assert params == ["decimation", "taps", "tapCount", "input", "output", "numOutputs", "cudaDevice", "cudaStream"]
+
+
+def test_headers_compile_as_c_and_cxx(tmp_path):
+    """fir.h must stay usable from plain C (the reference's is)."""
+    cuda_inc = "/usr/local/cuda/include"
+    if not Path(cuda_inc, "cuda_runtime.h").exists():
+        pytest.skip("CUDA headers not installed")
+    src = '#include <gsdr/fir.h>\n#include <gsdr/adjust_frequency.h>\n#include <gsdr/b200.h>\nint main(void){return 0;}\n'
+    for compiler, name in (("gcc", "t.c"), ("g++", "t.cpp")):
+        f = tmp_path / name
+        f.write_text(src)
+        subprocess.run([compiler, "-fsyntax-only", "-I", str(ROOT / "include"), "-I", cuda_inc, str(f)], check=True)
+
+
+def test_size_helpers_without_gpu():
+    import gsdr_b200 as g
+
+    assert g.fir_num_outputs(1 << 26, 255, 8) == 8_388_577  # BASELINE config 2
+    assert g.fir_num_outputs(1 << 20, 63, 1) == 1_048_514   # config 1
+    assert g.fir_num_outputs(1 << 28, 1023, 32) == 8_388_577  # config 3
+    assert g.fir_num_outputs(1 << 22, 127, 4) == 1_048_545  # config 4
+    assert g.fir_num_outputs(1 << 31, 255, 10) == 214_748_340  # config 5 stage 1
+    assert g.fir_num_outputs(10, 11, 1) == 0
+    assert g.fir_num_inputs(8_388_577, 255, 8) <= 1 << 26
+    assert g.fir_num_inputs(0, 255, 8) == 0
+
+
+def test_nco_phase_step_matches_oracle():
+    import gsdr_b200 as g
+    from oracle import oracle
+
+    for f, fs in [(100e3, 2.4e6), (-100e3, 2.4e6), (0.0, 1e6), (1.2e6, 2.4e6), (29520.0, 2.4e6), (7.0e6, 2.4e6)]:
+        assert g.nco_phase_step(f, fs) == oracle.nco_exact_phase_step(f, fs)

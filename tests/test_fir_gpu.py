@@ -1,0 +1,396 @@
+"""Parity tests proper: the sm_100a kernels, called through the C ABI, against the oracle (and against the
+reference's own CUDA kernels from oracle/_ref) on the same inputs.
+
+Tolerance (BASELINE.json north_star): max|err| <= 1e-5 * sum|h| * max|x| for FP32 results, because the
+accumulation order differs from the reference's single ascending chain.  The direct kernel (CC/CF and shapes the
+polyphase kernel cannot hold) keeps the reference's order and must match it bit for bit.
+"""
+import numpy as np
+import pytest
+import torch
+
+import gsdr_b200 as g
+from gsdr_b200 import synth
+from oracle import oracle, ref_cuda
+
+pytestmark = pytest.mark.gpu
+
+KIND_FN = {"ff": g.gsdrFirFF, "fc": g.gsdrFirFC, "cc": g.gsdrFirCC, "cf": g.gsdrFirCF}
+EDGE_SHAPES = [(1, 1), (2, 1), (1, 2), (16, 8), (8, 16), (31, 15), (32, 16), (33, 17)]  # ref: tests/test_fir.cpp:261-263
+
+
+def _rand(cplx, n, seed):
+    rng = np.random.default_rng(seed)
+    if cplx:
+        return (rng.uniform(-1, 1, n) + 1j * rng.uniform(-1, 1, n)).astype(np.complex64)
+    return rng.uniform(-1, 1, n).astype(np.float32)
+
+
+def _tol(taps, x):
+    return 1e-5 * float(np.abs(taps).sum()) * float(np.abs(x).max())
+
+
+def _run(kind, D, taps, x, n_out, dev, stream=None):
+    dt = torch.from_numpy(taps).to(dev)
+    dx = torch.from_numpy(x).to(dev)
+    out_dtype = torch.float32 if kind == "ff" else torch.complex64
+    # poison the output and keep guard elements around it to catch out-of-range stores
+    dy = torch.full((n_out + 16,), float("nan"), dtype=out_dtype, device=dev)
+    KIND_FN[kind](D, dt, taps.shape[0], dx, dy[8:], n_out, 0, stream)
+    torch.cuda.synchronize()
+    full = dy.cpu().numpy()
+    assert np.isnan(full[:8].real).all() and np.isnan(full[8 + n_out:].real).all(), "store outside [0, numOutputs)"
+    return full[8:8 + n_out]
+
+
+@pytest.fixture(autouse=True)
+def _auto_variant():
+    g.set_kernel_variant(-1)
+    yield
+    g.set_kernel_variant(-1)
+
+
+@pytest.mark.parametrize("kind", ["ff", "fc", "cc", "cf"])
+@pytest.mark.parametrize("T,n_out", EDGE_SHAPES)
+@pytest.mark.parametrize("D", [1, 2, 5])
+def test_edge_shapes(kind, T, n_out, D, cuda_device):
+    taps = _rand(kind[0] == "c", T, 100 + T)
+    x = _rand(kind[1] == "c", (n_out - 1) * D + T, 200 + n_out)
+    y = _run(kind, D, taps, x, n_out, cuda_device)
+    want = oracle.fir(kind, D, taps, x, n_out)
+    assert np.abs(y - want).max() <= _tol(taps, x)
+
+
+@pytest.mark.parametrize("kind", ["ff", "fc"])
+@pytest.mark.parametrize(
+    "D,T,n_in",
+    [
+        (1, 63, 1 << 20),       # BASELINE config 1 (FF) at full size
+        (8, 255, 1 << 20),      # config 2 shape, 1M samples
+        (32, 1023, 1 << 20),    # config 3 shape
+        (4, 127, 1 << 18),      # config 4 per-channel shape
+        (10, 255, 300_007),     # config 5 stage 1 (decimation not a power of two, ragged length)
+        (5, 63, 100_003),       # config 5 stage 3
+        (3, 1000, 50_000),      # many taps, odd decimation
+        (7, 5, 12_345),         # fewer taps than the decimation
+        (1, 1, 4097),
+        (64, 2047, 1 << 19),    # large D*T
+    ],
+)
+def test_polyphase_against_oracle(kind, D, T, n_in, cuda_device):
+    taps = synth.lowpass_taps(T, D) if T > 8 else _rand(False, T, 5)
+    x = synth.tone_plus_noise(0, n_in, seed=31, real=(kind == "ff"))
+    n_out = g.fir_num_outputs(n_in, T, D)
+    y = _run(kind, D, taps, x, n_out, cuda_device)
+    want = oracle.fir(kind, D, taps, x, n_out, threads=8)
+    err = np.abs(y - want).max()
+    assert err <= _tol(taps, x), f"max|err| {err}"
+    truth = oracle.fir(kind, D, taps, x, n_out, f64=True) if n_out * T < 5e8 else None
+    if truth is not None:
+        assert np.abs(y.astype(truth.dtype) - truth).max() <= _tol(taps, x)
+
+
+@pytest.mark.parametrize("variant", [-2, 0, 1, 2, 3, 4, 5])
+@pytest.mark.parametrize("kind", ["ff", "fc"])
+def test_every_kernel_variant(kind, variant, cuda_device):
+    D, T, n_in = 8, 255, 200_000
+    taps = synth.random_taps(T, 77)  # asymmetric: catches tap-order bugs
+    x = synth.tone_plus_noise(5, n_in, seed=32, real=(kind == "ff"))
+    n_out = g.fir_num_outputs(n_in, T, D) - 3  # ragged: last tile partly filled, input longer than needed
+    g.set_kernel_variant(variant)
+    info = g.describe_kernel(0 if kind == "fc" else 1, D, T, n_out)
+    assert info.variant == (variant if variant >= 0 else -1)
+    y = _run(kind, D, taps, x, n_out, cuda_device)
+    want = oracle.fir(kind, D, taps, x, n_out)
+    if variant == -2:
+        assert y.tobytes() == want.tobytes(), "direct kernel must reproduce the reference's accumulation order"
+    else:
+        assert np.abs(y - want).max() <= _tol(taps, x)
+
+
+@pytest.mark.parametrize("kind", ["cc", "cf", "fc", "ff"])
+def test_direct_kernel_is_bit_exact_to_the_reference_order(kind, cuda_device):
+    g.set_kernel_variant(-2)
+    D, T, n_out = 6, 300, 5000
+    taps = _rand(kind[0] == "c", T, 41)
+    x = _rand(kind[1] == "c", (n_out - 1) * D + T, 42)
+    y = _run(kind, D, taps, x, n_out, cuda_device)
+    assert y.tobytes() == oracle.fir(kind, D, taps, x, n_out).tobytes()
+
+
+def test_unaligned_pointers(cuda_device):
+    """cuComplex is only 8-byte aligned by the ABI; shard offsets are arbitrary sample offsets."""
+    D, T, n_out = 8, 255, 3000
+    taps = synth.lowpass_taps(T, D)
+    x = synth.tone_plus_noise(0, (n_out - 1) * D + T + 3, seed=33)
+    dt = torch.from_numpy(np.concatenate([np.zeros(1, np.float32), taps])).to(cuda_device)[1:]  # 4-byte aligned taps
+    dx = torch.from_numpy(x).to(cuda_device)
+    dy = torch.zeros(n_out + 1, dtype=torch.complex64, device=cuda_device)
+    for off in (1, 3):
+        g.gsdrFirFC(D, dt, T, dx[off:], dy[1:], n_out, 0, None)
+        torch.cuda.synchronize()
+        want = oracle.fir("fc", D, taps, x[off:], n_out)
+        assert np.abs(dy[1:].cpu().numpy() - want).max() <= _tol(taps, x)
+
+
+def test_impulse_and_dc_known_answers(cuda_device):
+    D, T, n_out = 8, 255, 2048
+    taps = synth.random_taps(T, 3)
+    n_in = (n_out - 1) * D + T
+    for k in (0, 254, 255, 8 * 1024 + 3, n_in - 1):
+        x = np.zeros(n_in, dtype=np.complex64)
+        x[k] = 1.0 + 2.0j
+        y = _run("fc", D, taps, x, n_out, cuda_device)
+        want = np.zeros(n_out, dtype=np.complex64)
+        for n in range(n_out):
+            i = k - n * D
+            if 0 <= i < T:
+                want[n] = taps[i] * x[k]
+        assert np.array_equal(y, want), f"impulse at {k}"
+    y = _run("fc", D, taps, np.ones(n_in, dtype=np.complex64), n_out, cuda_device)
+    assert np.abs(y - taps.astype(np.float64).sum()).max() <= _tol(taps, np.ones(1))
+
+
+def test_zero_taps_zero_outputs_and_bad_decimation(cuda_device):
+    dx = torch.ones(64, dtype=torch.complex64, device=cuda_device)
+    dy = torch.full((8,), 7.0, dtype=torch.complex64, device=cuda_device)
+    g.gsdrFirFC(2, None, 0, dx, dy, 8, 0, None)  # ref: tests/test_fir.cpp:249-257 — zero taps writes zeros
+    torch.cuda.synchronize()
+    assert (dy == 0).all()
+    dy.fill_(7.0)
+    g.gsdrFirFC(2, dx, 3, dx, dy, 0, 0, None)  # zero outputs: success, nothing written
+    torch.cuda.synchronize()
+    assert (dy == 7.0).all()
+    with pytest.raises(g.CudaError) as e:
+        g.gsdrFirFC(0, dx, 3, dx, dy, 4, 0, None)
+    assert e.value.code == 1  # cudaErrorInvalidValue
+
+
+def test_in_stream_semantics_and_graph_capture(cuda_device):
+    """Work goes to the given stream only and the call is capturable (no sync, no allocation)."""
+    D, T, n_in = 8, 255, 1 << 16
+    taps = synth.lowpass_taps(T, D)
+    x = synth.tone_plus_noise(0, n_in, seed=34)
+    n_out = g.fir_num_outputs(n_in, T, D)
+    dt, dx = torch.from_numpy(taps).to(cuda_device), torch.from_numpy(x).to(cuda_device)
+    dy = torch.zeros(n_out, dtype=torch.complex64, device=cuda_device)
+    s = torch.cuda.Stream()
+    g.gsdrFirFC(D, dt, T, dx, dy, n_out, 0, s)  # warm-up outside capture (sets the smem attribute)
+    s.synchronize()
+    dy.zero_()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph, stream=s):
+        g.gsdrFirFC(D, dt, T, dx, dy, n_out, 0, torch.cuda.current_stream())
+    assert (dy == 0).all(), "capture must not execute"
+    graph.replay()
+    torch.cuda.synchronize()
+    assert np.abs(dy.cpu().numpy() - oracle.fir("fc", D, taps, x, n_out)).max() <= _tol(taps, x)
+
+
+def test_current_device_is_preserved(cuda_device):
+    before = torch.cuda.current_device()
+    dx = torch.ones(300, dtype=torch.float32, device=cuda_device)
+    dy = torch.zeros(10, dtype=torch.float32, device=cuda_device)
+    g.gsdrFirFF(3, dx, 5, dx, dy, 10, 0, None)
+    torch.cuda.synchronize()
+    assert torch.cuda.current_device() == before
+    assert (dy == 5.0).all()
+    with pytest.raises(g.CudaError):
+        g.gsdrFirFF(3, dx, 5, dx, dy, 10, 99, None)  # no such device: error code, no crash
+    assert torch.cuda.current_device() == before
+
+
+# ---- batching and sharding --------------------------------------------------------------------------------
+
+@pytest.mark.parametrize("kind", ["fc", "ff"])
+@pytest.mark.parametrize("shared_taps", [True, False])
+def test_batched_channels_equal_single_calls_bit_exact(kind, shared_taps, cuda_device):
+    D, T, C, n_in = 4, 127, 9, 20_000
+    n_out = g.fir_num_outputs(n_in, T, D)
+    cplx = kind == "fc"
+    x = np.stack([synth.tone_plus_noise(c * 1000, n_in, seed=50 + c, real=not cplx) for c in range(C)])
+    taps = np.stack([synth.random_taps(T, 60 + (0 if shared_taps else c)) for c in range(C)])
+    dx, dt = torch.from_numpy(x).to(cuda_device), torch.from_numpy(taps).to(cuda_device)
+    out_dtype = torch.complex64 if cplx else torch.float32
+    dyb = torch.zeros((C, n_out + 5), dtype=out_dtype, device=cuda_device)
+    fnb = g.gsdrFirFCBatched if cplx else g.gsdrFirFFBatched
+    fnb(D, dt, T, 0 if shared_taps else T, dx, n_in, dyb, n_out + 5, n_out, C, 0, None)
+    dys = torch.zeros((C, n_out), dtype=out_dtype, device=cuda_device)
+    for c in range(C):
+        KIND_FN[kind](D, dt[c], T, dx[c], dys[c], n_out, 0, None)
+    torch.cuda.synchronize()
+    assert torch.equal(dyb[:, :n_out], dys)
+    assert (dyb[:, n_out:] == 0).all()
+    want = oracle.fir(kind, D, taps[3], x[3], n_out)
+    assert np.abs(dys[3].cpu().numpy() - want).max() <= _tol(taps[3], x[3])
+
+
+@pytest.mark.parametrize("shards", [2, 8])
+def test_time_shards_equal_unsharded_bit_exact(shards, cuda_device):
+    """BASELINE requirement: shard-vs-unsharded results identical (decimation phase and offsets bit-exact)."""
+    D, T, n_in = 8, 255, 1 << 20
+    fs, f, first = 2.4e6, 29520.0, 987_654_321
+    taps = synth.lowpass_taps(T, D)
+    dx = synth.tone_plus_noise(0, n_in, seed=35, device=cuda_device)
+    dt = torch.from_numpy(taps).to(cuda_device)
+    n_out = g.fir_num_outputs(n_in, T, D)
+    whole = torch.zeros(n_out, dtype=torch.complex64, device=cuda_device)
+    whole_nco = torch.zeros_like(whole)
+    g.gsdrFirFC(D, dt, T, dx, whole, n_out, 0, None)
+    g.gsdrAdjustFrequencyFirFC(fs, f, first, D, dt, T, dx, whole_nco, n_out, 0, None)
+    parts = torch.zeros_like(whole)
+    parts_nco = torch.zeros_like(whole)
+    for s in range(shards):
+        sh = g.shard_plan_time(n_out, D, T, first, shards, s)
+        xin = dx[sh.firstInput:sh.firstInput + sh.numInputs].clone()  # the shard's own resident copy (block + halo)
+        g.gsdrFirFC(D, dt, T, xin, parts[sh.firstOutput:], sh.numOutputs, 0, None)
+        g.gsdrAdjustFrequencyFirFC(fs, f, sh.firstSampleIndex, D, dt, T, xin, parts_nco[sh.firstOutput:],
+                                   sh.numOutputs, 0, None)
+    torch.cuda.synchronize()
+    assert torch.equal(parts, whole)
+    assert torch.equal(parts_nco, whole_nco)
+
+
+# ---- fused NCO --------------------------------------------------------------------------------------------
+
+@pytest.mark.parametrize("D,T,n_in", [(8, 255, 1 << 18), (32, 1023, 1 << 19), (10, 255, 100_003), (1, 31, 5000)])
+@pytest.mark.parametrize("first", [0, 77, 2 ** 40 + 12345])
+def test_nco_exact_against_oracle(D, T, n_in, first, cuda_device):
+    fs, f = 2.4e6, -310e3
+    taps = synth.lowpass_taps(T, D)
+    x = synth.tone_plus_noise(first, n_in, seed=36, tone_cycles_per_sample=310e3 / 2.4e6)
+    n_out = g.fir_num_outputs(n_in, T, D)
+    dt, dx = torch.from_numpy(taps).to(cuda_device), torch.from_numpy(x).to(cuda_device)
+    dy = torch.zeros(n_out, dtype=torch.complex64, device=cuda_device)
+    g.gsdrAdjustFrequencyFirFC(fs, f, first, D, dt, T, dx, dy, n_out, 0, None)
+    torch.cuda.synchronize()
+    y = dy.cpu().numpy()
+    n_chk = min(n_out, 4000)
+    want = oracle.adjust_frequency_fir_fc(oracle.NCO_EXACT, fs, f, first, D, taps, x, n_chk, f64=True)
+    assert np.abs(y[:n_chk] - want).max() <= _tol(taps, x)
+    # the +310 kHz tone lands at DC: |y| ~ amp * sum(h) = 0.5 everywhere, including the far end of the capture
+    mag = np.abs(y[T // D + 1:])
+    assert abs(float(mag.mean()) - 0.5) < 0.02 and float(mag.min()) > 0.4
+
+
+@pytest.mark.parametrize("first", [0, 5_000_003])
+def test_nco_literal_against_oracle(first, cuda_device):
+    fs, f, D, T, n_in = 2.4e6, 1.0e5, 8, 63, 50_000
+    taps = synth.random_taps(T, 8)
+    x = synth.tone_plus_noise(0, n_in, seed=37)
+    n_out = g.fir_num_outputs(n_in, T, D)
+    dt, dx = torch.from_numpy(taps).to(cuda_device), torch.from_numpy(x).to(cuda_device)
+    dy = torch.zeros(n_out, dtype=torch.complex64, device=cuda_device)
+    g.gsdrAdjustFrequencyFirFCLiteral(fs, f, first, D, dt, T, dx, dy, n_out, 0, None)
+    torch.cuda.synchronize()
+    want = oracle.adjust_frequency_fir_fc(oracle.NCO_LITERAL, fs, f, first, D, taps, x, n_out)
+    assert np.abs(dy.cpu().numpy() - want).max() <= _tol(taps, x)
+
+
+# ---- against the reference's own CUDA kernels (oracle/_ref) ------------------------------------------------
+
+needs_ref = pytest.mark.skipif(not ref_cuda.available(), reason="oracle/_ref/libgsdr_ref.so not built")
+
+
+@needs_ref
+@pytest.mark.parametrize("kind", ["ff", "fc", "cc", "cf"])
+@pytest.mark.parametrize("D,T,n_in", [(1, 63, 1 << 20), (8, 255, 1 << 22), (10, 255, 1_000_003), (32, 1023, 1 << 21)])
+def test_against_reference_cuda_kernels(kind, D, T, n_in, cuda_device):
+    taps = synth.random_taps(T, 70, complex_taps=(kind[0] == "c"))
+    taps = (taps / np.abs(taps).sum()).astype(taps.dtype)
+    dx = synth.tone_plus_noise(0, n_in, seed=38, device=cuda_device, real=(kind[1] == "f"))
+    dt = torch.from_numpy(taps).to(cuda_device)
+    n_out = g.fir_num_outputs(n_in, T, D)
+    out_dtype = torch.float32 if kind == "ff" else torch.complex64
+    ours = torch.zeros(n_out, dtype=out_dtype, device=cuda_device)
+    ref = torch.zeros(n_out, dtype=out_dtype, device=cuda_device)
+    KIND_FN[kind](D, dt, T, dx, ours, n_out, 0, None)
+    ref_cuda.fir(kind, D, dt, T, dx, ref, n_out)
+    torch.cuda.synchronize()
+    err = float((ours - ref).abs().max())
+    tol = 1e-5 * float(np.abs(taps).sum()) * float(dx.abs().max())
+    assert err <= tol, f"max|err| vs reference CUDA {err} > {tol}"
+    # and the oracle reproduces the reference's bits on a prefix
+    n_chk = min(n_out, 2000)
+    xh = dx[: (n_chk - 1) * D + T].cpu().numpy()
+    assert oracle.fir(kind, D, taps, xh, n_chk).tobytes() == ref[:n_chk].cpu().numpy().tobytes()
+
+
+@needs_ref
+def test_nco_literal_against_patched_reference_kernel(cuda_device):
+    fs, f, first, D, T, n_in = 2.4e6, 1.0e5, 5_000_003, 8, 255, 1 << 18
+    taps = synth.lowpass_taps(T, D)
+    dx = synth.tone_plus_noise(0, n_in, seed=39, device=cuda_device)
+    dt = torch.from_numpy(taps).to(cuda_device)
+    n_out = g.fir_num_outputs(n_in, T, D)
+    ours = torch.zeros(n_out, dtype=torch.complex64, device=cuda_device)
+    ref = torch.zeros_like(ours)
+    g.gsdrAdjustFrequencyFirFCLiteral(fs, f, first, D, dt, T, dx, ours, n_out, 0, None)
+    ref_cuda.adjust_frequency_fir_fc(fs, f, first, D, dt, T, dx, ref, n_out)
+    torch.cuda.synchronize()
+    tol = 1e-5 * float(np.abs(taps).sum()) * float(dx.abs().max())
+    assert float((ours - ref).abs().max()) <= tol
+
+
+# ---- host-buffer pipeline ---------------------------------------------------------------------------------
+
+def test_host_pipeline_equals_device_call_bit_exact(cuda_device):
+    D, T, n_in = 8, 255, 3_000_017
+    taps = synth.lowpass_taps(T, D)
+    x = synth.tone_plus_noise(0, n_in, seed=40)
+    n_out = g.fir_num_outputs(n_in, T, D)
+    xin = torch.from_numpy(x).pin_memory()
+    yout = torch.zeros(n_out, dtype=torch.complex64).pin_memory()
+    pipe = g.HostPipeline(0, chunkInputBytes=1 << 20, numBuffers=3)  # many chunks: exercises the block seams
+    pipe.gsdrFirFCHost(D, taps, T, xin, yout, n_out)
+    dy = torch.zeros(n_out, dtype=torch.complex64, device=cuda_device)
+    g.gsdrFirFC(D, torch.from_numpy(taps).to(cuda_device), T, xin.to(cuda_device), dy, n_out, 0, None)
+    torch.cuda.synchronize()
+    assert torch.equal(yout, dy.cpu())
+    z = torch.zeros(n_out, dtype=torch.complex64).pin_memory()
+    pipe.gsdrAdjustFrequencyFirFCHost(2.4e6, 29520.0, 11, D, taps, T, xin, z, n_out)
+    dz = torch.zeros_like(dy)
+    g.gsdrAdjustFrequencyFirFC(2.4e6, 29520.0, 11, D, torch.from_numpy(taps).to(cuda_device), T, xin.to(cuda_device),
+                               dz, n_out, 0, None)
+    torch.cuda.synchronize()
+    assert torch.equal(z, dz.cpu())
+    pipe.close()
+
+
+# ---- BASELINE full size, size-independent properties -------------------------------------------------------
+
+def test_config2_full_size_properties(cuda_device):
+    """64M cuComplex samples, 255 taps, decimate by 8: too big for the scalar oracle in seconds, so check
+    (a) a prefix and a suffix against the oracle, (b) linearity, (c) DC gain, (d) two-shard bit-exactness."""
+    D, T, n_in = 8, 255, 1 << 26
+    taps = synth.lowpass_taps(T, D)
+    dt = torch.from_numpy(taps).to(cuda_device)
+    dx = synth.tone_plus_noise(0, n_in, seed=0x5EED0002, device=cuda_device)
+    n_out = g.fir_num_outputs(n_in, T, D)
+    assert n_out == 8_388_577
+    dy = torch.zeros(n_out, dtype=torch.complex64, device=cuda_device)
+    g.gsdrFirFC(D, dt, T, dx, dy, n_out, 0, None)
+    torch.cuda.synchronize()
+    tol = 1e-5 * float(np.abs(taps).sum()) * float(dx.abs().max())
+    k = 4096
+    head = oracle.fir("fc", D, taps, dx[: (k - 1) * D + T].cpu().numpy(), k)
+    assert np.abs(dy[:k].cpu().numpy() - head).max() <= tol
+    tail_in = dx[(n_out - k) * D:].cpu().numpy()
+    tail = oracle.fir("fc", D, taps, tail_in, k)
+    assert np.abs(dy[n_out - k:].cpu().numpy() - tail).max() <= tol
+    # linearity: F(a*x) == a*F(x) for a power of two is exact in floating point
+    dy2 = torch.zeros_like(dy)
+    g.gsdrFirFC(D, dt, T, dx * 4.0, dy2, n_out, 0, None)
+    torch.cuda.synchronize()
+    assert torch.equal(dy2, dy * 4.0)
+    # two time shards reproduce the bits
+    parts = torch.zeros_like(dy)
+    for s in range(2):
+        sh = g.shard_plan_time(n_out, D, T, 0, 2, s)
+        g.gsdrFirFC(D, dt, T, dx[sh.firstInput:], parts[sh.firstOutput:], sh.numOutputs, 0, None)
+    torch.cuda.synchronize()
+    assert torch.equal(parts, dy)
+    del dy2, parts
+    # the in-band tone passes with |H| ~ 1: output power ~ amp^2
+    p = float((dy[64:].abs() ** 2).mean())
+    assert abs(p - 0.25) < 0.02
