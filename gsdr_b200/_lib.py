@@ -36,6 +36,8 @@ class KernelInfo(C.Structure):
         ("variant", C.c_int),
         ("outputsPerThread", C.c_int),
         ("threadsPerBlock", C.c_int),
+        ("phaseGroups", C.c_int),
+        ("windowBuffers", C.c_int),
         ("smCount", C.c_int),
         ("outputsPerBlock", c_size_t),
         ("sharedBytesPerBlock", c_size_t),
@@ -79,6 +81,7 @@ SIGNATURES = {
     "gsdrB200DescribeKernel": (C.c_int, [C.c_int, c_size_t, c_size_t, c_size_t, c_int32, C.POINTER(KernelInfo)]),
     "gsdrB200SetKernelVariant": (C.c_int, [C.c_int]),
     "gsdrB200NumKernelVariants": (C.c_int, []),
+    "gsdrB200SetDebugFlags": (C.c_int, [C.c_int]),
 }
 
 

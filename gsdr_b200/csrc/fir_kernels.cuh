@@ -14,7 +14,7 @@
 // sample is used by R FMAs and each tap by R FMAs.
 //
 // Shared-memory layout (per CTA, tile of BOUT = R*THREADS outputs):
-//     hs[D][Jpad]   floats, Jpad = J rounded up to a multiple of R, zero padded
+//     hs[D][Jpad]   floats, Jpad = J rounded up to a multiple of 2R, zero padded (+2R floats of zero slack)
 //     xs[D][pitch]  float2; element m of a row lives at position m + PAD*(m/R)  (PAD = 2 float2 of padding per R
 //                   elements, so a thread's 16-byte window loads are bank-conflict free: the per-thread stride is
 //                   (R+PAD)/2 = odd number of 16-byte units)
@@ -47,12 +47,14 @@ struct PolyParams {
   unsigned long long yStride;
   unsigned long long hStride;  // 0 = taps shared by all channels
   unsigned tilesPerChannel;
+  unsigned totalTiles;  // tilesPerChannel * numChannels
   unsigned D, T, Jpad, pitch;
   unsigned stageElems;  // (BOUT + Jpad) * D elements staged per (half-)tile
-  unsigned dp, dm;      // THREADS % D, THREADS / D
+  unsigned dp, dm;      // NT % D, NT / D   (NT = threads per CTA)
   unsigned posStep;     // shared-memory position step per staging iteration on the constant-stride path
   unsigned fastStage;   // 1 when dp == 0 and dm % R == 0 (every thread keeps its phase; positions advance uniformly)
   unsigned y16;         // output base and channel stride are 16-byte aligned
+  unsigned dbg;         // measurement hook (gsdrB200SetDebugFlags): bit0 = skip the window copies, bit1 = skip the FIR loop
   // NCO (kPolyNco*)
   unsigned long long ncoStep;   // phase increment per sample, cycles * 2^64
   unsigned long long ncoFirst;  // absolute sample index of input[0]
@@ -87,9 +89,9 @@ __device__ __forceinline__ void cpAsyncCommitWaitAll() {
   asm volatile("cp.async.wait_group 0;\n" ::: "memory");
 }
 
-// Stage `count` consecutive elements starting at global element index `g0` of channel base `src` into the
-// phase-major rows.  ELEM = 8 (float2 -> whole element) or 4 (float -> component `comp` of the element).
-template <int ELEM, int R, int THREADS>
+// Stage stageElems consecutive elements starting at global element index `g0` of channel base `src` into the
+// phase-major rows of one buffer.  ELEM = 8 (float2 -> whole element) or 4 (float -> component `comp`).
+template <int ELEM, int R, int NT>
 __device__ __forceinline__ void stageWindow(
     float2* xs, const unsigned char* src, unsigned long long g0, unsigned long long nIn, const PolyParams& P,
     unsigned comp) {
@@ -105,17 +107,17 @@ __device__ __forceinline__ void stageWindow(
     unsigned char* d = dstBase + (size_t)(p * P.pitch + polyPos(m, R)) * 8u;
     const unsigned dstep = P.posStep * 8u;
 #pragma unroll 8
-    for (unsigned s = tid; s < total; s += THREADS) {
+    for (unsigned s = tid; s < total; s += NT) {
       if (ELEM == 8) {
         cpAsync8(d, g);
       } else {
         cpAsync4(d, g);
       }
-      g += (size_t)THREADS * ELEM;
+      g += (size_t)NT * ELEM;
       d += dstep;
     }
   } else {
-    for (unsigned s = tid; s < total; s += THREADS) {
+    for (unsigned s = tid; s < total; s += NT) {
       const unsigned long long g = g0 + s;
       const bool valid = g < nIn;
       unsigned char* d = dstBase + (size_t)(p * P.pitch + polyPos(m, R)) * 8u;
@@ -137,11 +139,11 @@ __device__ __forceinline__ void stageWindow(
 
 // In-place NCO mix of the staged rows (runs after the async copies have landed, before the FIR loop).
 // Each thread walks elements of one row at a stride; element (p, m) is input sample in0 + m*D + p.
-template <int MODE, int R, int THREADS>
+template <int MODE, int R, int NT>
 __device__ __forceinline__ void mixWindow(float2* xs, unsigned long long in0, unsigned rowLen, const PolyParams& P) {
   const unsigned tid = threadIdx.x;
   const unsigned total = P.D * rowLen;
-  for (unsigned e = tid; e < total; e += THREADS) {
+  for (unsigned e = tid; e < total; e += NT) {
     const unsigned p = e / rowLen;
     const unsigned m = e - p * rowLen;
     const unsigned long long s = in0 + (unsigned long long)m * P.D + p;  // index relative to input[0]
@@ -167,127 +169,270 @@ __device__ __forceinline__ void mixWindow(float2* xs, unsigned long long in0, un
   }
 }
 
-template <int MODE, int R, int THREADS, int MINB>
-__global__ void __launch_bounds__(THREADS, MINB) firPolyKernel(const PolyParams P) {
+__device__ __forceinline__ void loadPair(float2& a, float2& b, const float2* src) {
+  const float4 v = *reinterpret_cast<const float4*>(src);
+  a = make_float2(v.x, v.y);
+  b = make_float2(v.z, v.w);
+}
+template <int R>
+__device__ __forceinline__ void loadSamples(float2 (&x)[R], const float2* src) {
+#pragma unroll
+  for (int k = 0; k < R; k += 2) loadPair(x[k], x[k + 1], src + k);
+}
+template <int R>
+__device__ __forceinline__ void loadTaps4(float (&h)[R], int off, const float* src) {
+  const float4 v = *reinterpret_cast<const float4*>(src);
+  h[off] = v.x;
+  h[off + 1] = v.y;
+  h[off + 2] = v.z;
+  h[off + 3] = v.w;
+}
+template <int R>
+__device__ __forceinline__ void loadTaps(float (&h)[R], const float* src) {
+#pragma unroll
+  for (int k = 0; k < R; k += 4) loadTaps4<R>(h, k, src + k);
+}
+__device__ __forceinline__ float2 macTap(float2 x, float h, float2 acc) {
+  return __ffma2_rn(x, make_float2(h, h), acc);  // FFMA2 acc, x.F32x2, h.F32 (scalar broadcast), acc
+}
+
+// The FIR inner loop is SAMPLE-stationary: window element e of a phase (sample xs[p][n0 + e]) is multiplied by
+// the R taps h[e - r], r = 0..R-1, into the R accumulators, then it is dead.  Consecutive FFMA2 therefore share
+// their sample operand (served by the operand-reuse cache), and each reads only its accumulator pair and one
+// tap from the register file: two registers per bank, so FFMA2 issues every 2 cycles.  (Tap-stationary order —
+// one tap, R samples — needs 5 distinct registers per FFMA2, 3 of them in one bank, and runs at 2/3 rate: measured
+// 61 % FMA-pipe utilisation, profiles/r01_notes.md.)  The taps slide through two register blocks of R.
+//
+// Elements of one phase (J' = Jpad taps, blocks of R):
+//   prologue   e = 0 .. R-1        element e feeds outputs r <= e            (taps block 0)
+//   steady b   e = R(b+1) + i      r <= i: new block b+1, slot i-r; r > i: old block b, slot R+i-r
+//   tail       e = J' + k, k<R-1   feeds outputs r > k                       (taps block J'/R - 1)
+
+// Block b+1 of samples in `x`; `ho` = tap block b (dies slot by slot, refilled with block b+2 from hNext),
+// `hn` = tap block b+1.  Each sample pair is refilled from xNext (same slots, two sample blocks ahead).
+template <int R>
+__device__ __forceinline__ void firSteady(
+    float2 (&acc)[R], float2 (&x)[R], float (&ho)[R], const float (&hn)[R], const float2* xNext, const float* hNext) {
+#pragma unroll
+  for (int i = 0; i < R; i++) {
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+      const float h = (r <= i) ? hn[(r <= i) ? i - r : 0] : ho[(r <= i) ? 0 : R + i - r];
+      acc[r] = macTap(x[i], h, acc[r]);
+    }
+    if (i & 1) loadPair(x[i - 1], x[i], xNext + (i - 1));
+    if ((i & 3) == 3) loadTaps4<R>(ho, i - 3, hNext + (i - 3));  // old slots <= i are dead after element i
+  }
+}
+template <int R>
+__device__ __forceinline__ void firPrologue(float2 (&acc)[R], const float2 (&x)[R], const float (&h0)[R]) {
+#pragma unroll
+  for (int e = 0; e < R; e++) {
+#pragma unroll
+    for (int r = 0; r <= e; r++) acc[r] = macTap(x[e], h0[e - r], acc[r]);
+  }
+}
+template <int R>
+__device__ __forceinline__ void firTail(float2 (&acc)[R], const float2 (&x)[R], const float (&hl)[R]) {
+#pragma unroll
+  for (int k = 0; k < R - 1; k++) {
+#pragma unroll
+    for (int r = k + 1; r < R; r++) acc[r] = macTap(x[k], hl[R + k - r], acc[r]);
+  }
+}
+
+// MODE: PolyMode.  R: outputs per thread.  TG: threads per phase group (tile = R*TG outputs).  PSPLIT: phase
+// groups; group g accumulates phases [g*D/PSPLIT, (g+1)*D/PSPLIT) and the partial sums are added through shared
+// memory.  NBUF: sample-window buffers (2 = the next tile is copied in while this one is filtered).
+// Persistent: each CTA walks tiles blockIdx.x, blockIdx.x + gridDim.x, ...
+template <int MODE, int R, int TG, int PSPLIT, int NBUF, int MINB>
+__global__ void __launch_bounds__(TG* PSPLIT, MINB) firPolyKernel(const PolyParams P) {
   static_assert(R % 4 == 0 && R >= 4, "R must be a multiple of 4");
-  constexpr unsigned BOUT = R * THREADS;
+  static_assert(NBUF == 1 || NBUF == 2, "one or two window buffers");
+  constexpr unsigned NT = TG * PSPLIT;
+  constexpr unsigned BOUT = R * TG;
   constexpr bool kReal = (MODE == kPolyFF);
+  constexpr unsigned kTileOut = kReal ? 2u * BOUT : BOUT;
   extern __shared__ __align__(16) unsigned char smemRaw[];
-  float* hs = reinterpret_cast<float*>(smemRaw);                                       // [D][Jpad] (+R slack)
-  float2* xs = reinterpret_cast<float2*>(smemRaw + ((size_t)P.D * P.Jpad + R) * 4u);  // [D][pitch]
+  float* hs = reinterpret_cast<float*>(smemRaw);  // [D][Jpad] (+2R slack)
+  float2* xsBase = reinterpret_cast<float2*>(smemRaw + ((size_t)P.D * P.Jpad + 2 * R) * 4u);
+  const unsigned bufElems = P.D * P.pitch;  // float2 per buffer
 
   const unsigned tid = threadIdx.x;
-  const unsigned chan = blockIdx.x / P.tilesPerChannel;
-  const unsigned tile = blockIdx.x - chan * P.tilesPerChannel;
-  const unsigned long long o0 = (unsigned long long)tile * (kReal ? 2u * BOUT : BOUT);
-  const unsigned long long in0 = o0 * P.D;
-  const float* h = P.h + (size_t)chan * P.hStride;
+  const unsigned grp = tid / TG;
+  const unsigned t = tid - grp * TG;
+  const unsigned pBegin = (grp * P.D) / PSPLIT;
+  const unsigned pEnd = ((grp + 1) * P.D) / PSPLIT;
+  const unsigned elemBytes = kReal ? 4u : 8u;
 
-  // ---- stage the sample window (async, no registers) ----
-  if (kReal) {
-    const unsigned char* src = reinterpret_cast<const unsigned char*>(P.x) + (size_t)chan * P.xStride * 4u;
-    stageWindow<4, R, THREADS>(xs, src, in0, P.nIn, P, 0u);
-    stageWindow<4, R, THREADS>(xs, src, in0 + (unsigned long long)BOUT * P.D, P.nIn, P, 1u);
-  } else {
-    const unsigned char* src = reinterpret_cast<const unsigned char*>(P.x) + (size_t)chan * P.xStride * 8u;
-    stageWindow<8, R, THREADS>(xs, src, in0, P.nIn, P, 0u);
-  }
-  // ---- taps -> phase-major, zero padded (overlaps with the copies in flight) ----
-  {
-    const unsigned nh = P.D * P.Jpad;
-    for (unsigned i = tid; i < nh + R; i += THREADS) {
-      const unsigned p = i / P.Jpad;
-      const unsigned j = i - p * P.Jpad;
-      const unsigned ti = j * P.D + p;
-      hs[i] = (i < nh && ti < P.T) ? __ldg(h + ti) : 0.0f;
+  auto stageTile = [&](unsigned work, float2* xs) {
+    if (P.dbg & 1u) return;
+    const unsigned chan = work / P.tilesPerChannel;
+    const unsigned tile = work - chan * P.tilesPerChannel;
+    const unsigned long long in0 = (unsigned long long)tile * kTileOut * P.D;
+    const unsigned char* src = reinterpret_cast<const unsigned char*>(P.x) + (size_t)chan * P.xStride * elemBytes;
+    if (kReal) {
+      stageWindow<4, R, NT>(xs, src, in0, P.nIn, P, 0u);
+      stageWindow<4, R, NT>(xs, src, in0 + (unsigned long long)BOUT * P.D, P.nIn, P, 1u);
+    } else {
+      stageWindow<8, R, NT>(xs, src, in0, P.nIn, P, 0u);
     }
+  };
+
+  unsigned work = blockIdx.x;
+  if (NBUF == 2) {
+    if (work < P.totalTiles) stageTile(work, xsBase);
+    asm volatile("cp.async.commit_group;\n" ::: "memory");
   }
-  cpAsyncCommitWaitAll();
-  __syncthreads();
-  if (MODE == kPolyNcoExact || MODE == kPolyNcoLiteral) {
-    mixWindow<MODE, R, THREADS>(xs, in0, BOUT + P.Jpad, P);
-    __syncthreads();
-  }
+  unsigned tapsChan = 0xffffffffu;
 
-  // ---- polyphase FIR: R outputs per thread, sliding register window ----
-  float2 acc[R];
-#pragma unroll
-  for (int r = 0; r < R; r++) acc[r] = make_float2(0.0f, 0.0f);
+  for (unsigned it = 0; work < P.totalTiles; work += gridDim.x, it++) {
+    float2* xs = xsBase + (NBUF == 2 ? (it & 1u) * bufElems : 0u);
+    const unsigned chan = work / P.tilesPerChannel;
+    const unsigned tile = work - chan * P.tilesPerChannel;
+    const unsigned long long o0 = (unsigned long long)tile * kTileOut;
 
-  const float2* xrow = xs + (size_t)tid * (R + kPolyPad);
-  const float* hp = hs;
-  float4 hnext[R / 4];
-#pragma unroll
-  for (int k = 0; k < R / 4; k++) hnext[k] = *reinterpret_cast<const float4*>(hp + 4 * k);
-
-  for (unsigned p = 0; p < P.D; p++, xrow += P.pitch) {
-    const float2* xp = xrow;
-    float2 w[R];
-#pragma unroll
-    for (int k = 0; k < R; k += 2) {
-      const float4 v = *reinterpret_cast<const float4*>(xp + k);
-      w[k] = make_float2(v.x, v.y);
-      w[k + 1] = make_float2(v.z, v.w);
+    if (NBUF == 2) {
+      const unsigned nextWork = work + gridDim.x;
+      if (nextWork < P.totalTiles) stageTile(nextWork, xsBase + ((it + 1u) & 1u) * bufElems);
+      asm volatile("cp.async.commit_group;\n" ::: "memory");
+    } else {
+      stageTile(work, xs);
+      asm volatile("cp.async.commit_group;\n" ::: "memory");
     }
-    xp += R + kPolyPad;
-    for (unsigned j0 = 0; j0 < P.Jpad; j0 += R, xp += R + kPolyPad) {
-      float hv[R];
-#pragma unroll
-      for (int k = 0; k < R / 4; k++) {
-        hv[4 * k + 0] = hnext[k].x;
-        hv[4 * k + 1] = hnext[k].y;
-        hv[4 * k + 2] = hnext[k].z;
-        hv[4 * k + 3] = hnext[k].w;
-      }
-      hp += R;  // rows of hs are contiguous, so this also walks into the next phase; R floats of slack at the end
-#pragma unroll
-      for (int k = 0; k < R / 4; k++) hnext[k] = *reinterpret_cast<const float4*>(hp + 4 * k);
-#pragma unroll
-      for (int jj = 0; jj < R; jj++) {
-        const float2 hh = make_float2(hv[jj], hv[jj]);
-#pragma unroll
-        for (int r = 0; r < R; r++) acc[r] = __ffma2_rn(w[(jj + r) % R], hh, acc[r]);
-        if (jj & 1) {
-          const float4 v = *reinterpret_cast<const float4*>(xp + (jj - 1));
-          w[jj - 1] = make_float2(v.x, v.y);
-          w[jj] = make_float2(v.z, v.w);
+    // taps -> phase-major, zero padded; once per CTA unless the channel (and its tap set) changes
+    if (chan != tapsChan && (tapsChan == 0xffffffffu || P.hStride != 0)) {
+      const float* h = P.h + (size_t)chan * P.hStride;
+      const unsigned nh = P.D * P.Jpad;
+      unsigned p = tid / P.Jpad;
+      unsigned j = tid - p * P.Jpad;
+      const unsigned dpj = NT / P.Jpad, djj = NT - dpj * P.Jpad;
+      for (unsigned i = tid; i < nh + 2 * R; i += NT) {
+        const unsigned ti = j * P.D + p;
+        hs[i] = (i < nh && ti < P.T) ? __ldg(h + ti) : 0.0f;
+        p += dpj;
+        j += djj;
+        if (j >= P.Jpad) {
+          j -= P.Jpad;
+          p += 1;
         }
       }
     }
-  }
+    tapsChan = chan;
+    if (NBUF == 2) {
+      asm volatile("cp.async.wait_group 1;\n" ::: "memory");
+    } else {
+      asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+    }
+    __syncthreads();
+    if (MODE == kPolyNcoExact || MODE == kPolyNcoLiteral) {
+      mixWindow<MODE, R, NT>(xs, o0 * P.D, BOUT + P.Jpad, P);
+      __syncthreads();
+    }
 
-  // ---- store ----
-  const unsigned long long ob = o0 + (unsigned long long)tid * R;
-  if (!kReal) {
-    float2* y = reinterpret_cast<float2*>(P.y) + (size_t)chan * P.yStride;
-    if (P.y16 && ob + R <= P.nOut) {
+    // ---- polyphase FIR: R outputs per thread, sample-stationary, taps sliding through registers ----
+    float2 acc[R];
 #pragma unroll
-      for (int r = 0; r < R; r += 2) {
-        *reinterpret_cast<float4*>(y + ob + r) = make_float4(acc[r].x, acc[r].y, acc[r + 1].x, acc[r + 1].y);
-      }
-    } else {
-#pragma unroll
-      for (int r = 0; r < R; r++) {
-        if (ob + r < P.nOut) y[ob + r] = acc[r];
+    for (int r = 0; r < R; r++) acc[r] = make_float2(0.0f, 0.0f);
+    const unsigned pStop = (P.dbg & 2u) ? pBegin : pEnd;
+    if (pBegin < pStop) {
+      constexpr unsigned BLK = R + kPolyPad;  // float2 positions per block of R samples
+      const float2* xrow = xs + (size_t)t * BLK + (size_t)pBegin * P.pitch;
+      const float* hp = hs + (size_t)pBegin * P.Jpad;
+      const unsigned nbk = P.Jpad / R;  // even, >= 2
+      float hA[R], hB[R];
+      float2 xA[R], xB[R], xC[R];
+      loadTaps<R>(hA, hp);
+      loadTaps<R>(hB, hp + R);
+      loadSamples<R>(xC, xrow);
+      loadSamples<R>(xB, xrow + BLK);
+      for (unsigned p = pBegin; p < pStop; p++, xrow += P.pitch, hp += P.Jpad) {
+        const bool more = p + 1 < pStop;
+        const float2* xrowNext = more ? xrow + P.pitch : xrow;  // last phase: harmless re-read of this row
+        firPrologue<R>(acc, xC, hA);
+        loadSamples<R>(xA, xrow + 2 * BLK);
+        const float2* xq = xrow + 3 * BLK;
+        const float* hq = hp + 2 * R;
+        for (unsigned b = 0; b + 2 < nbk; b += 2) {
+          firSteady<R>(acc, xB, hA, hB, xq, hq);
+          firSteady<R>(acc, xA, hB, hA, xq + BLK, hq + R);
+          xq += 2 * BLK;
+          hq += 2 * R;
+        }
+        // last steady block of the phase: its refills already fetch the NEXT phase (tap rows are contiguous, so
+        // hq points at the next phase's block 0; samples come from the next row's block 1), and block 0 of the
+        // next row goes to xC, which has been free since the prologue.
+        loadSamples<R>(xC, xrowNext);
+        firSteady<R>(acc, xB, hA, hB, xrowNext + BLK, hq);
+        firTail<R>(acc, xA, hB);
+        loadTaps<R>(hB, hq + R);
       }
     }
-  } else {
-    float* y = reinterpret_cast<float*>(P.y) + (size_t)chan * P.yStride;
-    const unsigned long long ob2 = ob + BOUT;
-    if (P.y16 && ob2 + R <= P.nOut) {
+
+    // ---- add the phase groups' partial sums (fixed order: deterministic) ----
+    if (PSPLIT > 1) {
+      __syncthreads();  // everyone is done reading this window; reuse it as scratch
+      float4* red = reinterpret_cast<float4*>(xs);
+      if (grp > 0) {
 #pragma unroll
-      for (int r = 0; r < R; r += 4) {
-        *reinterpret_cast<float4*>(y + ob + r) = make_float4(acc[r].x, acc[r + 1].x, acc[r + 2].x, acc[r + 3].x);
-        *reinterpret_cast<float4*>(y + ob2 + r) = make_float4(acc[r].y, acc[r + 1].y, acc[r + 2].y, acc[r + 3].y);
+        for (int q = 0; q < R / 2; q++) {
+          red[((grp - 1) * (R / 2) + q) * TG + t] =
+              make_float4(acc[2 * q].x, acc[2 * q].y, acc[2 * q + 1].x, acc[2 * q + 1].y);
+        }
       }
-    } else {
+      __syncthreads();
+      if (grp == 0) {
 #pragma unroll
-      for (int r = 0; r < R; r++) {
-        if (ob + r < P.nOut) y[ob + r] = acc[r].x;
-        if (ob2 + r < P.nOut) y[ob2 + r] = acc[r].y;
+        for (int g = 1; g < PSPLIT; g++) {
+#pragma unroll
+          for (int q = 0; q < R / 2; q++) {
+            const float4 v = red[((g - 1) * (R / 2) + q) * TG + t];
+            acc[2 * q].x += v.x;
+            acc[2 * q].y += v.y;
+            acc[2 * q + 1].x += v.z;
+            acc[2 * q + 1].y += v.w;
+          }
+        }
       }
     }
+
+    // ---- store ----
+    if (grp == 0) {
+      const unsigned long long ob = o0 + (unsigned long long)t * R;
+      if (!kReal) {
+        float2* y = reinterpret_cast<float2*>(P.y) + (size_t)chan * P.yStride;
+        if (P.y16 && ob + R <= P.nOut) {
+#pragma unroll
+          for (int r = 0; r < R; r += 2) {
+            *reinterpret_cast<float4*>(y + ob + r) = make_float4(acc[r].x, acc[r].y, acc[r + 1].x, acc[r + 1].y);
+          }
+        } else {
+#pragma unroll
+          for (int r = 0; r < R; r++) {
+            if (ob + r < P.nOut) y[ob + r] = acc[r];
+          }
+        }
+      } else {
+        float* y = reinterpret_cast<float*>(P.y) + (size_t)chan * P.yStride;
+        const unsigned long long ob2 = ob + BOUT;
+        if (P.y16 && ob2 + R <= P.nOut) {
+#pragma unroll
+          for (int r = 0; r < R; r += 4) {
+            *reinterpret_cast<float4*>(y + ob + r) = make_float4(acc[r].x, acc[r + 1].x, acc[r + 2].x, acc[r + 3].x);
+            *reinterpret_cast<float4*>(y + ob2 + r) = make_float4(acc[r].y, acc[r + 1].y, acc[r + 2].y, acc[r + 3].y);
+          }
+        } else {
+#pragma unroll
+          for (int r = 0; r < R; r++) {
+            if (ob + r < P.nOut) y[ob + r] = acc[r].x;
+            if (ob2 + r < P.nOut) y[ob2 + r] = acc[r].y;
+          }
+        }
+      }
+    }
+    __syncthreads();  // the window (and the scratch in it) is free before anyone refills it
   }
+  asm volatile("cp.async.wait_group 0;\n" ::: "memory");
 }
 
 // ---------------------------------------------------------------------------------------------------------

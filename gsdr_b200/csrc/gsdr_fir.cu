@@ -22,6 +22,7 @@ namespace gsdr_b200 {
 static cudaError_t report(cudaError_t st, const char* what) noexcept {
   if (st != cudaSuccess) {
     std::fprintf(stderr, "gsdr-b200: error %d - %s - %s\n", (int)st, cudaGetErrorName(st), what);
+    (void)cudaGetLastError();  // the error is returned to the caller; do not leave it in the runtime's last-error slot
   }
   return st;
 }
@@ -50,18 +51,32 @@ uint64_t ncoPhaseStep(float frequencyShift, float sampleRate) noexcept {
 // polyphase kernel variants
 // ---------------------------------------------------------------------------------------------------------
 struct PolyVariant {
-  int R, threads, minBlocks;
+  int R, tg, psplit, nbuf, minBlocks;
+  int threads() const { return tg * psplit; }
 };
+// X(id, R, TG, PSPLIT, NBUF, MINB)
+#define GSDR_POLY_VARIANTS(X) \
+  X(0, 8, 128, 1, 1, 2)       \
+  X(1, 8, 64, 1, 1, 3)        \
+  X(2, 8, 32, 1, 1, 4)        \
+  X(3, 8, 64, 2, 2, 2)        \
+  X(4, 8, 64, 2, 1, 2)        \
+  X(5, 8, 128, 1, 2, 1)       \
+  X(6, 8, 64, 1, 2, 2)        \
+  X(7, 8, 32, 4, 2, 2)        \
+  X(8, 16, 64, 1, 1, 2)       \
+  X(9, 8, 32, 2, 2, 4)        \
+  X(10, 8, 128, 2, 1, 2)      \
+  X(11, 8, 64, 4, 2, 2)
+
 static constexpr PolyVariant kVariants[] = {
-    {8, 128, 2},  // 0: 1024 outputs / CTA
-    {8, 64, 3},   // 1:  512
-    {8, 32, 4},   // 2:  256
-    {16, 64, 2},  // 3: 1024, deeper register tile
-    {8, 256, 1},  // 4: 2048
-    {16, 128, 1}, // 5: 2048
+#define X(id, r, tg, ps, nb, mb) {r, tg, ps, nb, mb},
+    GSDR_POLY_VARIANTS(X)
+#undef X
 };
 static constexpr int kNumVariants = (int)(sizeof(kVariants) / sizeof(kVariants[0]));
 
+static std::atomic<int> gDebugFlags{0};
 static std::atomic<int> gForcedVariant{-1};  // -1 auto, -2 direct kernel, >=0 variant id (test/tuning hook)
 
 struct DeviceInfo {
@@ -90,51 +105,59 @@ struct PolyGeom {
 
 static bool polyGeometry(const PolyVariant& v, size_t D, size_t T, PolyGeom* g) noexcept {
   const size_t R = (size_t)v.R;
+  if (D > 4096 || D < (size_t)v.psplit) return false;
   const size_t J = (T + D - 1) / D;
-  const size_t Jpad = (J + R - 1) / R * R;
-  const size_t bout = R * (size_t)v.threads;
-  const size_t rowElems = bout + Jpad;
-  size_t pitch = polyPos((unsigned)(rowElems - 1), (unsigned)R) + 1;
+  const size_t Jpad = (J + 2 * R - 1) / (2 * R) * (2 * R);  // the tap loop is unrolled over two register blocks
+  const size_t bout = R * (size_t)v.tg;
+  const size_t rowStaged = bout + Jpad;
+  const size_t rowAlloc = rowStaged + R;  // the refills run one block of samples past the last one used
+  size_t pitch = polyPos((unsigned)(rowAlloc - 1), (unsigned)R) + 1;
   while (pitch % 4 != 2) pitch++;  // even (16-byte rows) and == 2 mod 4 (staging stores spread over banks)
-  const size_t smem = (D * Jpad + R) * 4 + D * pitch * 8;
-  if (D > 4096 || Jpad > (1u << 20) || smem > (size_t)1 << 20) return false;
+  if (Jpad > (1u << 20)) return false;
+  const size_t smem = (D * Jpad + 2 * R) * 4 + (size_t)v.nbuf * D * pitch * 8;
+  if (smem > (size_t)1 << 20) return false;
   g->Jpad = (unsigned)Jpad;
   g->pitch = (unsigned)pitch;
-  g->stageElems = (unsigned)(rowElems * D);
+  g->stageElems = (unsigned)(rowStaged * D);
   g->smemBytes = smem;
   return true;
 }
 
-template <int MODE, int R, int THREADS, int MINB>
-static cudaError_t launchPolyT(const PolyParams& P, unsigned grid, size_t smem, int dev, cudaStream_t stream) noexcept {
+template <int MODE, int R, int TG, int PSPLIT, int NBUF, int MINB>
+static cudaError_t launchPolyT(PolyParams& P, size_t smem, int dev, int smCount, cudaStream_t stream) noexcept {
   static std::atomic<unsigned long long> configured{0};  // bit per device
-  auto kernel = firPolyKernel<MODE, R, THREADS, MINB>;
+  static std::atomic<int> occCache[64];                  // CTAs per SM at the max dynamic smem actually used
+  auto kernel = firPolyKernel<MODE, R, TG, PSPLIT, NBUF, MINB>;
   const unsigned long long bit = 1ull << (dev & 63);
   if (!(configured.load(std::memory_order_acquire) & bit)) {
     cudaError_t st = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (st != cudaSuccess) return report(st, "cudaFuncSetAttribute(MaxDynamicSharedMemorySize)");
     configured.fetch_or(bit, std::memory_order_release);
   }
-  kernel<<<grid, THREADS, smem, stream>>>(P);
-  return cudaGetLastError();
+  (void)occCache;
+  int perSm = 0;
+  cudaError_t st = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, kernel, TG * PSPLIT, smem);
+  if (st != cudaSuccess) return report(st, "cudaOccupancyMaxActiveBlocksPerMultiprocessor");
+  if (perSm < 1) return cudaErrorInvalidConfiguration;
+  const unsigned long long resident = (unsigned long long)perSm * (unsigned)smCount;
+  const unsigned grid = (unsigned)(P.totalTiles < resident ? P.totalTiles : resident);
+  void* args[] = {(void*)&P};
+  return cudaLaunchKernel((const void*)kernel, dim3(grid), dim3(TG * PSPLIT), args, smem, stream);
 }
 
 template <int MODE>
-static cudaError_t launchPolyMode(int variant, const PolyParams& P, unsigned grid, size_t smem, int dev,
+static cudaError_t launchPolyMode(int variant, PolyParams& P, size_t smem, int dev, int smCount,
                                   cudaStream_t stream) noexcept {
   switch (variant) {
-    case 0: return launchPolyT<MODE, 8, 128, 2>(P, grid, smem, dev, stream);
-    case 1: return launchPolyT<MODE, 8, 64, 3>(P, grid, smem, dev, stream);
-    case 2: return launchPolyT<MODE, 8, 32, 4>(P, grid, smem, dev, stream);
-    case 3: return launchPolyT<MODE, 16, 64, 2>(P, grid, smem, dev, stream);
-    case 4: return launchPolyT<MODE, 8, 256, 1>(P, grid, smem, dev, stream);
-    case 5: return launchPolyT<MODE, 16, 128, 1>(P, grid, smem, dev, stream);
+#define X(id, r, tg, ps, nb, mb) \
+  case id: return launchPolyT<MODE, r, tg, ps, nb, mb>(P, smem, dev, smCount, stream);
+    GSDR_POLY_VARIANTS(X)
+#undef X
     default: return cudaErrorInvalidValue;
   }
 }
 
-// Choose the variant with the largest tile that still lets two CTAs share an SM; fall back to one CTA per SM,
-// then to smaller tiles.  Returns -1 when no variant fits in shared memory.
+// Automatic choice: first variant of the preference list whose shared memory fits.
 static int choosePolyVariant(size_t D, size_t T, size_t nOut, int maxSmem, PolyGeom* geom) noexcept {
   const int forced = gForcedVariant.load(std::memory_order_relaxed);
   if (forced == -2) return -1;
@@ -142,14 +165,13 @@ static int choosePolyVariant(size_t D, size_t T, size_t nOut, int maxSmem, PolyG
     return (polyGeometry(kVariants[forced], D, T, geom) && geom->smemBytes <= (size_t)maxSmem) ? forced : -1;
   }
   (void)nOut;
-  static const int order[] = {0, 1, 2};
-  const size_t twoPerSm = (size_t)(228 * 1024 - 2 * 1024) / 2;
-  for (int pass = 0; pass < 2; pass++) {
+  static const int order[] = {1, 2};
+  const size_t budgets[] = {(size_t)44 * 1024, (size_t)(226 * 1024) / 2, (size_t)maxSmem};
+  for (size_t limit : budgets) {
     for (int id : order) {
       PolyGeom g;
       if (!polyGeometry(kVariants[id], D, T, &g)) continue;
-      const size_t limit = pass == 0 ? twoPerSm : (size_t)maxSmem;
-      if (g.smemBytes <= limit) {
+      if (g.smemBytes <= limit && g.smemBytes <= (size_t)maxSmem) {
         *geom = g;
         return id;
       }
@@ -174,8 +196,9 @@ static cudaError_t launchDirect(const FirCall& c, cudaStream_t stream) noexcept 
   const unsigned long long grid = bpc * c.numChannels;
   if (bpc > 0x7fffffffull || grid > 0x7fffffffull) return cudaErrorInvalidValue;
   P.blocksPerChannel = (unsigned)bpc;
-  firDirectKernel<IN_T, OUT_T, TAP_T><<<(unsigned)grid, kDirectThreads, 0, stream>>>(P);
-  return cudaGetLastError();
+  void* args[] = {(void*)&P};
+  return cudaLaunchKernel((const void*)firDirectKernel<IN_T, OUT_T, TAP_T>, dim3((unsigned)grid),
+                          dim3(kDirectThreads), args, 0, stream);
 }
 
 static size_t outElemBytes(FirType t) noexcept { return t == kFirFF ? 4 : 8; }
@@ -214,10 +237,10 @@ cudaError_t enqueueFir(const FirCall& c, cudaStream_t stream) noexcept {
   }
 
   const PolyVariant& v = kVariants[variant];
-  const size_t bout = (size_t)v.R * v.threads * (c.type == kFirFF ? 2 : 1);
+  const size_t bout = (size_t)v.R * v.tg * (c.type == kFirFF ? 2 : 1);
   const unsigned long long tiles = (c.numOutputs + bout - 1) / bout;
-  const unsigned long long grid = tiles * c.numChannels;
-  if (tiles > 0x7fffffffull || grid > 0x7fffffffull) return cudaErrorInvalidValue;
+  const unsigned long long total = tiles * c.numChannels;
+  if (tiles > 0x7fffffffull || total > 0x7fffffffull) return cudaErrorInvalidValue;
 
   PolyParams P{};
   P.x = c.input;
@@ -229,28 +252,32 @@ cudaError_t enqueueFir(const FirCall& c, cudaStream_t stream) noexcept {
   P.yStride = c.outputStride;
   P.hStride = c.tapStride;
   P.tilesPerChannel = (unsigned)tiles;
+  P.totalTiles = (unsigned)total;
   P.D = (unsigned)c.decimation;
   P.T = (unsigned)c.tapCount;
   P.Jpad = geom.Jpad;
   P.pitch = geom.pitch;
   P.stageElems = geom.stageElems;
-  P.dp = (unsigned)(v.threads % c.decimation);
-  P.dm = (unsigned)(v.threads / c.decimation);
+  const unsigned nt = (unsigned)v.threads();
+  P.dp = (unsigned)(nt % c.decimation);
+  P.dm = (unsigned)(nt / c.decimation);
   P.fastStage = (P.dp == 0 && P.dm % v.R == 0 && P.dm > 0) ? 1u : 0u;
   P.posStep = P.dm + kPolyPad * (P.dm / v.R);
   const size_t oe = outElemBytes(c.type);
   P.y16 = ((uintptr_t)c.output % 16 == 0 && (c.numChannels == 1 || (c.outputStride * oe) % 16 == 0)) ? 1u : 0u;
+  P.dbg = (unsigned)gDebugFlags.load(std::memory_order_relaxed);
   P.ncoStep = ncoPhaseStep(c.frequencyShift, c.sampleRate);
   P.ncoFirst = c.firstSampleIndex;
   P.ncoFirst32 = (uint32_t)fmodf((float)c.firstSampleIndex, c.sampleRate);  // ref: src/fm.cu:202
   P.ncoFs = c.sampleRate;
   P.ncoF = c.frequencyShift;
 
-  if (c.type == kFirFF) return launchPolyMode<kPolyFF>(variant, P, (unsigned)grid, geom.smemBytes, dev, stream);
+  const int sms = info->smCount;
+  if (c.type == kFirFF) return launchPolyMode<kPolyFF>(variant, P, geom.smemBytes, dev, sms, stream);
   switch (c.nco) {
-    case kNcoNone: return launchPolyMode<kPolyFC>(variant, P, (unsigned)grid, geom.smemBytes, dev, stream);
-    case kNcoExact: return launchPolyMode<kPolyNcoExact>(variant, P, (unsigned)grid, geom.smemBytes, dev, stream);
-    case kNcoLiteral: return launchPolyMode<kPolyNcoLiteral>(variant, P, (unsigned)grid, geom.smemBytes, dev, stream);
+    case kNcoNone: return launchPolyMode<kPolyFC>(variant, P, geom.smemBytes, dev, sms, stream);
+    case kNcoExact: return launchPolyMode<kPolyNcoExact>(variant, P, geom.smemBytes, dev, sms, stream);
+    case kNcoLiteral: return launchPolyMode<kPolyNcoLiteral>(variant, P, geom.smemBytes, dev, sms, stream);
   }
   return cudaErrorInvalidValue;
 }
@@ -353,6 +380,11 @@ GSDR_C_LINKAGE int gsdrB200SetKernelVariant(int variant) GSDR_NO_EXCEPT {
 
 GSDR_C_LINKAGE int gsdrB200NumKernelVariants(void) GSDR_NO_EXCEPT { return kNumVariants; }
 
+GSDR_C_LINKAGE int gsdrB200SetDebugFlags(int flags) GSDR_NO_EXCEPT {
+  gDebugFlags.store(flags & 3, std::memory_order_relaxed);
+  return 0;
+}
+
 GSDR_C_LINKAGE int gsdrB200DescribeKernel(int firType, size_t decimation, size_t tapCount, size_t numOutputs,
                                           int32_t cudaDevice, gsdrB200KernelInfo* info) GSDR_NO_EXCEPT {
   if (!info || decimation == 0) return -1;
@@ -369,9 +401,11 @@ GSDR_C_LINKAGE int gsdrB200DescribeKernel(int firType, size_t decimation, size_t
   const int v = polyType ? choosePolyVariant(decimation, tapCount, numOutputs, di->maxSmemOptin, &g) : -1;
   info->variant = v;
   if (v >= 0) {
-    const size_t bout = (size_t)kVariants[v].R * kVariants[v].threads * (firType == kFirFF ? 2 : 1);
+    const size_t bout = (size_t)kVariants[v].R * kVariants[v].tg * (firType == kFirFF ? 2 : 1);
     info->outputsPerThread = kVariants[v].R;
-    info->threadsPerBlock = kVariants[v].threads;
+    info->threadsPerBlock = kVariants[v].threads();
+    info->phaseGroups = kVariants[v].psplit;
+    info->windowBuffers = kVariants[v].nbuf;
     info->outputsPerBlock = bout;
     info->sharedBytesPerBlock = g.smemBytes;
     info->numBlocks = (numOutputs + bout - 1) / bout;

@@ -165,6 +165,8 @@ typedef struct gsdrB200KernelInfo {
   int variant;          /* polyphase variant id, or -1 for the direct (one output per thread) kernel */
   int outputsPerThread; /* R */
   int threadsPerBlock;
+  int phaseGroups;      /* thread groups that split the polyphase branches of a tile (partial sums added on chip) */
+  int windowBuffers;    /* 2: the next tile's window is copied in while the current one is filtered */
   int smCount;
   size_t outputsPerBlock;
   size_t sharedBytesPerBlock;
@@ -186,5 +188,10 @@ GSDR_C_LINKAGE GSDR_PUBLIC int gsdrB200DescribeKernel(
  */
 GSDR_C_LINKAGE GSDR_PUBLIC int gsdrB200SetKernelVariant(int variant) GSDR_NO_EXCEPT;
 GSDR_C_LINKAGE GSDR_PUBLIC int gsdrB200NumKernelVariants(void) GSDR_NO_EXCEPT;
+/*
+ * Measurement hook (results are WRONG while set): bit 0 skips the global->shared window copies, bit 1 skips the
+ * FIR loop.  Lets a profiler time the two halves of the kernel separately.  0 restores normal operation.
+ */
+GSDR_C_LINKAGE GSDR_PUBLIC int gsdrB200SetDebugFlags(int flags) GSDR_NO_EXCEPT;
 
 #endif /* GSDR_B200_INCLUDE_GSDR_B200_H_ */

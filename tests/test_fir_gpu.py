@@ -90,7 +90,7 @@ def test_polyphase_against_oracle(kind, D, T, n_in, cuda_device):
         assert np.abs(y.astype(truth.dtype) - truth).max() <= _tol(taps, x)
 
 
-@pytest.mark.parametrize("variant", [-2, 0, 1, 2, 3, 4, 5])
+@pytest.mark.parametrize("variant", [-2] + list(range(12)))
 @pytest.mark.parametrize("kind", ["ff", "fc"])
 def test_every_kernel_variant(kind, variant, cuda_device):
     D, T, n_in = 8, 255, 200_000
@@ -100,6 +100,7 @@ def test_every_kernel_variant(kind, variant, cuda_device):
     g.set_kernel_variant(variant)
     info = g.describe_kernel(0 if kind == "fc" else 1, D, T, n_out)
     assert info.variant == (variant if variant >= 0 else -1)
+    assert g.num_kernel_variants() == 12
     y = _run(kind, D, taps, x, n_out, cuda_device)
     want = oracle.fir(kind, D, taps, x, n_out)
     if variant == -2:
@@ -269,8 +270,9 @@ def test_nco_exact_against_oracle(D, T, n_in, first, cuda_device):
     want = oracle.adjust_frequency_fir_fc(oracle.NCO_EXACT, fs, f, first, D, taps, x, n_chk, f64=True)
     assert np.abs(y[:n_chk] - want).max() <= _tol(taps, x)
     # the +310 kHz tone lands at DC: |y| ~ amp * sum(h) = 0.5 everywhere, including the far end of the capture
+    # (the wider the filter, i.e. the smaller D, the more of the sigma = 0.1 noise rides on it)
     mag = np.abs(y[T // D + 1:])
-    assert abs(float(mag.mean()) - 0.5) < 0.02 and float(mag.min()) > 0.4
+    assert abs(float(mag.mean()) - 0.5) < 0.02 and float(mag.min()) > 0.25
 
 
 @pytest.mark.parametrize("first", [0, 5_000_003])

@@ -42,6 +42,7 @@ def main():
     ap.add_argument("--kind", default="fc")
     ap.add_argument("--ref", action="store_true")
     ap.add_argument("--peaks", action="store_true")
+    ap.add_argument("--split", action="store_true", help="also time copy-only and FIR-only halves of each variant")
     args = ap.parse_args()
     dev = torch.device("cuda:0")
     torch.cuda.set_device(dev)
@@ -60,6 +61,12 @@ def main():
         lib = ctypes.CDLL(str(ROOT / "tools" / "libubench_fp32.so"))
         lib.ubenchFp32Tflops.restype = ctypes.c_double
         lib.ubenchFp32Tflops.argtypes = [ctypes.c_int] * 5
+        lib.ubenchFirShapeTflops.restype = ctypes.c_double
+        lib.ubenchFirShapeTflops.argtypes = [ctypes.c_int] * 5
+        for bps in (1, 2, 4, 8):
+            print(json.dumps({"peak": "fir-shaped operands, 128-thread blocks", "blocks_per_sm": bps,
+                              "ffma2_tflops": lib.ubenchFirShapeTflops(0, 0, 8000, 3, bps),
+                              "ffma_tflops": lib.ubenchFirShapeTflops(1, 0, 8000, 3, bps)}), flush=True)
         for bps in (1, 2, 4, 8):
             print(json.dumps({"peak": "fp32", "blocks_per_sm": bps, "ffma_tflops": lib.ubenchFp32Tflops(0, 0, 8000, 3, bps),
                               "ffma2_tflops": lib.ubenchFp32Tflops(1, 0, 8000, 3, bps)}), flush=True)
@@ -75,7 +82,14 @@ def main():
         if ref is None:
             ref = y.clone()
         diff = float((y - ref).abs().max())
-        print(json.dumps({"variant": v, "threads": info.threadsPerBlock, "R": info.outputsPerThread,
+        extra = {}
+        if args.split and v >= 0:
+            from gsdr_b200._lib import lib as _l
+            for name, flag in (("ms_copy_only", 2), ("ms_fir_only", 1)):
+                _l.gsdrB200SetDebugFlags(flag)
+                extra[name] = timeit(lambda: fn(D, taps, T, x, y, n_out, 0, stream), stream, reps=10)[0]
+            _l.gsdrB200SetDebugFlags(0)
+        print(json.dumps({"variant": v, **extra, "threads": info.threadsPerBlock, "R": info.outputsPerThread,
                           "smem": info.sharedBytesPerBlock, "ctas": info.numBlocks, "ms_median": med, "ms_best": best,
                           "msamples_s": n_in / med / 1e3, "gbs": bytes_alg / med / 1e6, "tflops": flops / med / 1e9,
                           "maxdiff_vs_first": diff}), flush=True)

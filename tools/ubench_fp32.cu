@@ -64,11 +64,222 @@ extern "C" double ubenchFp32Tflops(int packed, int device, int iters, int reps, 
   return best;
 }
 
+// FIR-shaped operand pattern: 8 accumulator pairs, a 16-pair register window, 8 scalar taps; each FFMA2 is
+// acc[r] += w[jj+r] * h[jj] exactly as in firBlockStep, but with no memory traffic.  Shows whether the register
+// file can feed FFMA2 at the pipe rate with this operand mix (mode 0), and the scalar-FFMA equivalent (mode 1).
+template <int MODE>
+__global__ void __launch_bounds__(128) k_firshape(float* out, int iters, float seed) {
+  float2 acc[8], w[16];
+  float h[8];
+#pragma unroll
+  for (int i = 0; i < 8; i++) acc[i] = make_float2(threadIdx.x * 1e-3f + i, blockIdx.x * 1e-3f - i);
+#pragma unroll
+  for (int i = 0; i < 16; i++) w[i] = make_float2(seed + i, seed - i);
+#pragma unroll
+  for (int i = 0; i < 8; i++) h[i] = seed * (i + 1);
+  for (int it = 0; it < iters; it++) {
+#pragma unroll
+    for (int jj = 0; jj < 8; jj++) {
+#pragma unroll
+      for (int r = 0; r < 8; r++) {
+        if (MODE == 0) {
+          acc[r] = __ffma2_rn(w[jj + r], make_float2(h[jj], h[jj]), acc[r]);
+        } else {
+          acc[r].x = __fmaf_rn(w[jj + r].x, h[jj], acc[r].x);
+          acc[r].y = __fmaf_rn(w[jj + r].y, h[jj], acc[r].y);
+        }
+      }
+    }
+    // rotate the window a little so nothing is loop invariant
+#pragma unroll
+    for (int i = 0; i < 8; i++) h[i] = -h[i];
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; i++) s += acc[i].x + acc[i].y;
+  if (s == 123.456f) out[0] = s;
+}
+
+// Same FIR-shaped loop, but the 8 taps live in VECTOR registers (values loaded per thread) so every FFMA2 reads
+// 5 vector registers.  MODE 2: sample-stationary order (consecutive FFMA2 share the sample pair);
+// MODE 3: tap-stationary order (consecutive FFMA2 share the tap); MODE 4: like 2 but the taps are made uniform
+// with a warp reduction (REDUX -> uniform register).
+template <int MODE>
+__global__ void __launch_bounds__(128) k_firshape_v(float* out, const float* in, int iters) {
+  float2 acc[8], w[16];
+  float h[16];
+#pragma unroll
+  for (int i = 0; i < 8; i++) acc[i] = make_float2(threadIdx.x * 1e-3f + i, blockIdx.x * 1e-3f - i);
+#pragma unroll
+  for (int i = 0; i < 16; i++) w[i] = make_float2(in[threadIdx.x * 32 + i], in[threadIdx.x * 32 + 16 + i]);
+#pragma unroll
+  for (int i = 0; i < 16; i++) {
+    h[i] = in[4096 + threadIdx.x * 16 + i];
+    if (MODE == 4) h[i] = __uint_as_float(__reduce_or_sync(0xffffffffu, __float_as_uint(h[i])));
+  }
+  for (int it = 0; it < iters; it++) {
+    if (MODE == 3) {
+#pragma unroll
+      for (int jj = 0; jj < 8; jj++) {
+#pragma unroll
+        for (int r = 0; r < 8; r++) acc[r] = __ffma2_rn(w[jj + r], make_float2(h[jj], h[jj]), acc[r]);
+      }
+    } else {
+#pragma unroll
+      for (int e = 0; e < 8; e++) {
+#pragma unroll
+        for (int r = 0; r < 8; r++) acc[r] = __ffma2_rn(w[e], make_float2(h[8 + e - r], h[8 + e - r]), acc[r]);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 16; i++) w[i].x = -w[i].x;
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; i++) s += acc[i].x + acc[i].y;
+  if (s == 123.456f) out[0] = s;
+}
+
+// Issue-slot test: the sample-stationary FFMA2 block (64 FFMA2, vector taps) with K extra ALU-pipe integer
+// instructions (LOP3/SHF/IADD3 on private registers) mixed in per block.  If an FFMA2 only needs one issue slot
+// per two pipe cycles, K up to ~64 is free; if it holds the issue port for both cycles, throughput falls as
+// 128 / (128 + K).
+template <int K>
+__global__ void __launch_bounds__(128) k_issue(float* out, const float* in, int iters) {
+  float2 acc[8], w[8];
+  float h[16];
+  unsigned u[8];
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    acc[i] = make_float2(threadIdx.x * 1e-3f + i, blockIdx.x * 1e-3f - i);
+    w[i] = make_float2(in[threadIdx.x * 32 + i], in[threadIdx.x * 32 + 16 + i]);
+    u[i] = threadIdx.x * 977u + i;
+  }
+#pragma unroll
+  for (int i = 0; i < 16; i++) h[i] = in[4096 + threadIdx.x * 16 + i];
+  for (int it = 0; it < iters; it++) {
+#pragma unroll
+    for (int e = 0; e < 8; e++) {
+#pragma unroll
+      for (int r = 0; r < 8; r++) {
+        acc[r] = __ffma2_rn(w[e], make_float2(h[8 + e - r], h[8 + e - r]), acc[r]);
+        if ((e * 8 + r) * K / 64 != (e * 8 + r + 1) * K / 64) {
+          const int q = (e * 8 + r) & 7;
+          u[q] = (u[q] ^ (u[q] >> 3)) + 0x9E3779B9u;  // LOP3 + SHF + IADD3: count each source line as ~2-3 ALU ops
+        }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; i++) w[i].x = -w[i].x;
+  }
+  float s = 0.f;
+  unsigned v = 0;
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    s += acc[i].x + acc[i].y;
+    v ^= u[i];
+  }
+  if (s == 123.456f || v == 0x12345u) out[0] = s;
+}
+
+extern "C" double ubenchIssueTflops(int k, int device, int iters, int reps, int blocksPerSm) {
+  int prev = 0, sms = 0;
+  if (cudaGetDevice(&prev) != cudaSuccess) return -1.0;
+  if (cudaSetDevice(device) != cudaSuccess) return -2.0;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+  float* out = nullptr;
+  cudaMalloc(&out, 4);
+  float* in = nullptr;
+  cudaMalloc(&in, 65536);
+  cudaMemset(in, 0, 65536);
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  const int grid = sms * blocksPerSm;
+  double best = 0.0;
+  for (int r = 0; r < reps + 1; r++) {
+    cudaEventRecord(e0);
+    switch (k) {
+      case 0: k_issue<0><<<grid, 128>>>(out, in, iters); break;
+      case 8: k_issue<8><<<grid, 128>>>(out, in, iters); break;
+      case 16: k_issue<16><<<grid, 128>>>(out, in, iters); break;
+      case 32: k_issue<32><<<grid, 128>>>(out, in, iters); break;
+      default: k_issue<64><<<grid, 128>>>(out, in, iters); break;
+    }
+    cudaEventRecord(e1);
+    if (cudaEventSynchronize(e1) != cudaSuccess) { best = -3.0; break; }
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    const double flops = 2.0 * 2.0 * 64.0 * (double)iters * 128.0 * (double)grid;
+    const double tf = flops / (ms * 1e-3) / 1e12;
+    if (r > 0 && tf > best) best = tf;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(out);
+  cudaFree(in);
+  cudaSetDevice(prev);
+  return best;
+}
+
+extern "C" double ubenchFirShapeTflops(int mode, int device, int iters, int reps, int blocksPerSm) {
+  int prev = 0, sms = 0;
+  if (cudaGetDevice(&prev) != cudaSuccess) return -1.0;
+  if (cudaSetDevice(device) != cudaSuccess) return -2.0;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+  float* out = nullptr;
+  cudaMalloc(&out, 4);
+  float* in = nullptr;
+  cudaMalloc(&in, 65536);
+  cudaMemset(in, 0, 65536);
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  const int grid = sms * blocksPerSm;
+  double best = 0.0;
+  for (int r = 0; r < reps + 1; r++) {
+    cudaEventRecord(e0);
+    if (mode == 0) k_firshape<0><<<grid, 128>>>(out, iters, 0.5f);
+    else if (mode == 1) k_firshape<1><<<grid, 128>>>(out, iters, 0.5f);
+    else if (mode == 2) k_firshape_v<2><<<grid, 128>>>(out, in, iters);
+    else if (mode == 3) k_firshape_v<3><<<grid, 128>>>(out, in, iters);
+    else k_firshape_v<4><<<grid, 128>>>(out, in, iters);
+    cudaEventRecord(e1);
+    if (cudaEventSynchronize(e1) != cudaSuccess) { best = -3.0; break; }
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    const double flops = 2.0 * 2.0 * 64.0 * (double)iters * 128.0 * (double)grid;
+    const double tf = flops / (ms * 1e-3) / 1e12;
+    if (r > 0 && tf > best) best = tf;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(out);
+  cudaFree(in);
+  cudaSetDevice(prev);
+  return best;
+}
+
 #ifdef UBENCH_MAIN
 int main() {
   for (int bps = 1; bps <= 8; bps *= 2) {
     printf("blocks/SM %d: FFMA %.2f TFLOP/s, FFMA2 %.2f TFLOP/s\n", bps, ubenchFp32Tflops(0, 0, 20000, 3, bps),
            ubenchFp32Tflops(1, 0, 20000, 3, bps));
+  }
+  for (int bps = 1; bps <= 8; bps *= 2) {
+    printf("FIR-shaped, 128-thread blocks/SM %d: FFMA2 %.2f TFLOP/s, scalar FFMA %.2f TFLOP/s\n", bps,
+           ubenchFirShapeTflops(0, 0, 20000, 3, bps), ubenchFirShapeTflops(1, 0, 20000, 3, bps));
+  }
+  for (int bps = 1; bps <= 8; bps *= 2) {
+    printf("vector taps, blocks/SM %d: sample-stationary %.2f, tap-stationary %.2f, REDUX-uniform taps %.2f TFLOP/s\n",
+           bps, ubenchFirShapeTflops(2, 0, 20000, 3, bps), ubenchFirShapeTflops(3, 0, 20000, 3, bps),
+           ubenchFirShapeTflops(4, 0, 20000, 3, bps));
+  }
+  for (int bps = 2; bps <= 8; bps *= 2) {
+    printf("issue test, blocks/SM %d: 64 FFMA2 + K int-op lines: K=0 %.2f, K=8 %.2f, K=16 %.2f, K=32 %.2f, K=64 %.2f TFLOP/s\n", bps,
+           ubenchIssueTflops(0, 0, 20000, 3, bps), ubenchIssueTflops(8, 0, 20000, 3, bps),
+           ubenchIssueTflops(16, 0, 20000, 3, bps), ubenchIssueTflops(32, 0, 20000, 3, bps),
+           ubenchIssueTflops(64, 0, 20000, 3, bps));
   }
   return 0;
 }
