@@ -21,6 +21,7 @@ from .api import (  # noqa: F401
     nco_phase_step,
     set_kernel_variant,
     num_kernel_variants,
+    num_polyphase_variants,
     shard_plan_channels,
     shard_plan_time,
 )

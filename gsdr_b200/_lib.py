@@ -81,6 +81,7 @@ SIGNATURES = {
     "gsdrB200DescribeKernel": (C.c_int, [C.c_int, c_size_t, c_size_t, c_size_t, c_int32, C.POINTER(KernelInfo)]),
     "gsdrB200SetKernelVariant": (C.c_int, [C.c_int]),
     "gsdrB200NumKernelVariants": (C.c_int, []),
+    "gsdrB200NumPolyphaseVariants": (C.c_int, []),
     "gsdrB200SetDebugFlags": (C.c_int, [C.c_int]),
 }
 

@@ -139,6 +139,10 @@ def num_kernel_variants() -> int:
     return int(lib.gsdrB200NumKernelVariants())
 
 
+def num_polyphase_variants() -> int:
+    return int(lib.gsdrB200NumPolyphaseVariants())
+
+
 class HostPipeline:
     """gsdrHostPipeline: host buffers in, host buffers out, H2D / kernel / D2H overlapped chunk by chunk."""
 

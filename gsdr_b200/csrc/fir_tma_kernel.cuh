@@ -1,0 +1,441 @@
+// fir_tma_kernel.cuh — the fast path for complex input x real taps (gsdrFirFC and the fused NCO stage):
+// a persistent, TMA-fed polyphase FIR for even decimations with rows of at most 128 bytes (D <= 16).
+// Replaces ref: src/fir.cu:49-71 (k_FirDecimate<cuComplex,cuComplex,float>) and the per-tap arithmetic of
+// ref: src/adjustFrequency.cu:36-55.
+//
+// Why TMA.  On sm_100a an FFMA2 holds the issue port for two cycles and EVERY other instruction costs one more
+// (tools/ubench_fp32.cu, profiles/r01_notes.md), so the FIR is bound by issue slots, not by the FMA pipe alone.
+// Staging the window with per-thread cp.async costs ~6 issue cycles per 32 samples; a TMA tensor copy costs
+// none: one elected thread issues ONE cp.async.bulk.tensor per tile and the copy engine does the rest at HBM speed
+// (6.7 TB/s measured for this box shape, tools/tma_probe.cu).
+//
+// Shared-memory layout of one window buffer.  The input is viewed as rows of D samples (row m = samples
+// m*D .. m*D+D-1, G = 8*D bytes).  A 3-D tensor map (row bytes | mh, stride 8 rows | ml, stride 1 row) with box
+// (G bytes, MHP, 8) lands the window as
+//        buf[ml][mh][G bytes],        m = 8*mh + ml,
+// i.e. eight planes holding every 8th row.  A thread owns outputs n0 = 8*t .. 8*t+7 of the tile, so the sample it
+// needs for window element e = 8*c + i is row (ml = i, mh = t + c): consecutive lanes read consecutive mh — G
+// bytes apart.  Rows whose 16-byte chunk count (D/2) is odd are bank-conflict free as they are; for D = 4, 8, 16
+// the TMA swizzle mode (32/64/128 B) XORs the chunk index with row-address bits and the reader applies the same
+// XOR, which makes the eight 16-byte loads of a quarter warp hit eight different bank groups.
+//
+// Inner loop.  One LDS.128 fetches the samples of two adjacent polyphase branches (2*pp, 2*pp+1) of one row; it
+// feeds 2 x 8 FFMA2 (sample-stationary: consecutive FFMA2 share the sample operand).  Taps of the two branches
+// are stored interleaved, hs2[pp][j] = (h[j*D+2pp], h[j*D+2pp+1]), contiguous across pairs, and slide through
+// two register blocks.  Samples run through a ring of 8 float4 registers, loaded 6 elements ahead.
+#pragma once
+
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "fir_kernels.cuh"
+
+namespace gsdr_b200 {
+
+struct TmaParams {
+  const float2* x;  // channel 0 input (edge tiles and unaligned fallbacks read it directly)
+  const float* h;
+  float2* y;
+  unsigned long long nOut, nIn;
+  unsigned long long xStride, yStride, hStride;
+  unsigned tilesPerChannel, totalTiles, numChannels;
+  unsigned strideChan, strideTile;  // gridDim.x split as strideChan * tilesPerChannel + strideTile
+  unsigned D, T, Jpad;
+  unsigned rowBytes;     // G = 8*D
+  unsigned mhp;          // rows per plane in a buffer (box dim 1)
+  unsigned planeBytes;   // mhp * G, a multiple of 1024
+  unsigned swzShift;     // address bit the chunk XOR takes its source from, relative to mh: see tmaSwizzle()
+  unsigned swzMask;      // 0 (no swizzle), 1, 3 or 7
+  unsigned tmaRows;      // rows visible to TMA per channel (multiple of 8); windows reaching past it use cp.async
+  unsigned y16;
+  unsigned dbg;
+  unsigned long long ncoStep, ncoFirst;
+  unsigned ncoFirst32;
+  float ncoFs, ncoF;
+};
+
+constexpr int kTmaR = 8;
+constexpr unsigned kTmaJpadCap = 64;  // compile-time-geometry kernels hold up to 64 taps per branch (T <= 64*D)
+
+// Rows per plane of a window buffer: TG row groups for the outputs + Jpad/8 for the taps' reach, rounded so
+// that a plane is a whole number of swizzle periods (swizzled rows) or of 128-byte TMA units (plain rows).
+__host__ __device__ constexpr unsigned tmaPlaneRows(unsigned tg, unsigned jpad, unsigned D) {
+  const unsigned G = 8u * D;
+  const unsigned unit = (G == 32u) ? 256u : (G == 64u) ? 512u : (G == 128u) ? 1024u : 128u;
+  unsigned mhp = tg + jpad / 8u;
+  while ((mhp * G) % unit) mhp++;
+  return mhp;
+}
+
+// XOR applied to the 16-byte chunk index of row-group mh (what the TMA swizzle modes do to address bits 4..6):
+//   32B  mode (G = 32):  chunk ^= addr bit 7      = (mh >> 2) & 1
+//   64B  mode (G = 64):  chunk ^= addr bits 7..8  = (mh >> 1) & 3
+//   128B mode (G = 128): chunk ^= addr bits 7..9  =  mh       & 7
+// DT is the compile-time decimation (0 = take everything from the parameter block).
+template <int DT>
+__device__ __forceinline__ unsigned tmaSwizzle(unsigned mh, const TmaParams& P) {
+  if (DT == 4) return (mh >> 2) & 1u;
+  if (DT == 8) return (mh >> 1) & 3u;
+  if (DT == 16) return mh & 7u;
+  if (DT != 0) return 0u;
+  return (mh >> P.swzShift) & P.swzMask;
+}
+
+// byte offset inside a buffer of sample (row m, phase p)
+template <int DT>
+__device__ __forceinline__ unsigned tmaSampleOffset(unsigned m, unsigned p, unsigned planeBytes, const TmaParams& P) {
+  const unsigned mh = m >> 3;
+  const unsigned rowBytes = DT ? 8u * DT : P.rowBytes;
+  return (m & 7u) * planeBytes + mh * rowBytes + ((((p >> 1) ^ tmaSwizzle<DT>(mh, P))) << 4) + (p & 1u) * 8u;
+}
+
+__device__ __forceinline__ unsigned smemU32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbarInit(unsigned long long* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smemU32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbarExpectTx(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smemU32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbarArrive(unsigned long long* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smemU32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbarWait(unsigned long long* bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(smemU32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tmaLoad4(void* dst, const CUtensorMap* map, unsigned long long* bar, int c0, int c1,
+                                         int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], "
+      "[%2];" ::"r"(smemU32(dst)),
+      "l"(map), "r"(smemU32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+
+enum TmaBlockKind : int { kBlkPrologue = 0, kBlkSteady = 1, kBlkTail = 2 };
+
+// One block of 8 window elements of a branch pair.  q[]: sample ring (slot = element index & 7).
+// hnP/hnQ: taps block b ("new") of branches P/Q, hoP/hoQ: taps block b-1 ("old").  Element i feeds output r with
+// tap (i-r) of the new block when r <= i, with tap (8+i-r) of the old block when r > i.  After element i its ring
+// slot is free: the element six ahead is loaded (planes 6,7 of this block from a0, planes 0..5 of the next block
+// from a1).  Old-tap slots i-1, i are dead after odd i and are refilled with the block after `new` (tapNext).
+template <int KIND, bool REFILL_TAPS>
+__device__ __forceinline__ void firPairBlock(
+    float2 (&acc)[kTmaR], float4 (&q)[8], float (&hoP)[8], float (&hoQ)[8], const float (&hnP)[8],
+    const float (&hnQ)[8], const unsigned char* a0, const unsigned char* a1, unsigned planeBytes,
+    const float* tapNext) {
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    if (!(KIND == kBlkTail && i == 7)) {
+      const float2 xP = make_float2(q[i].x, q[i].y);
+      const float2 xQ = make_float2(q[i].z, q[i].w);
+#pragma unroll
+      for (int r = 0; r < kTmaR; r++) {
+        const bool useNew = r <= i;
+        if ((useNew && KIND != kBlkTail) || (!useNew && KIND != kBlkPrologue)) {
+          const float h = useNew ? hnP[useNew ? i - r : 0] : hoP[useNew ? 0 : 8 + i - r];
+          acc[r] = macTap(xP, h, acc[r]);
+        }
+      }
+#pragma unroll
+      for (int r = 0; r < kTmaR; r++) {
+        const bool useNew = r <= i;
+        if ((useNew && KIND != kBlkTail) || (!useNew && KIND != kBlkPrologue)) {
+          const float h = useNew ? hnQ[useNew ? i - r : 0] : hoQ[useNew ? 0 : 8 + i - r];
+          acc[r] = macTap(xQ, h, acc[r]);
+        }
+      }
+    }
+    // sample six elements ahead -> the ring slot that element (i-2) vacated
+    {
+      const int e = i + 6;
+      const bool skip = (KIND == kBlkTail && e == 7);  // element 7 of the tail block is never used
+      if (!skip) {
+        const unsigned char* addr = (e < 8) ? a0 + (unsigned)e * planeBytes : a1 + (unsigned)(e - 8) * planeBytes;
+        q[e & 7] = *reinterpret_cast<const float4*>(addr);
+      }
+    }
+    if (REFILL_TAPS && (i & 1)) {
+      const float4 v = *reinterpret_cast<const float4*>(tapNext + 2 * (i - 1));
+      hoP[i - 1] = v.x;
+      hoQ[i - 1] = v.y;
+      hoP[i] = v.z;
+      hoQ[i] = v.w;
+    }
+  }
+}
+
+// Slow stager for windows that reach past the TMA-visible rows (the last tile(s) of a channel): same layout,
+// 8-byte cp.async with zero fill beyond the caller-guaranteed extent.
+template <int NT, int DT>
+__device__ __forceinline__ void tmaStageSlow(unsigned char* buf, const float2* src, unsigned long long in0,
+                                             unsigned rows, unsigned planeBytes, const TmaParams& P) {
+  const unsigned D = DT ? (unsigned)DT : P.D;
+  const unsigned total = rows * D;
+  unsigned p = threadIdx.x % D, m = threadIdx.x / D;
+  const unsigned dp = NT % D, dm = NT / D;
+  for (unsigned s = threadIdx.x; s < total; s += NT) {
+    const unsigned long long g = in0 + s;
+    const bool valid = g < P.nIn;
+    cpAsync8z(buf + tmaSampleOffset<DT>(m, p, planeBytes, P), src + (valid ? g : 0ull), valid);
+    p += dp;
+    m += dm;
+    if (p >= D) {
+      p -= D;
+      m += 1;
+    }
+  }
+}
+
+// In-place NCO mix of a landed window (all threads).  Element (m, p) is input sample in0 + m*D + p.
+template <int MODE, int NT, int DT>
+__device__ __forceinline__ void tmaMixWindow(unsigned char* buf, unsigned long long in0, unsigned rows,
+                                             unsigned planeBytes, const TmaParams& P) {
+  const unsigned D = DT ? (unsigned)DT : P.D;
+  const unsigned pairsPerRow = D >> 1;
+  const unsigned total = rows * pairsPerRow;
+  for (unsigned e = threadIdx.x; e < total; e += NT) {
+    const unsigned m = e / pairsPerRow;
+    const unsigned pp = e - m * pairsPerRow;
+    float4* q = reinterpret_cast<float4*>(buf + tmaSampleOffset<DT>(m, 2 * pp, planeBytes, P));
+    float4 v = *q;
+    float sn[2], cs[2];
+#pragma unroll
+    for (int k = 0; k < 2; k++) {
+      const unsigned long long s = in0 + (unsigned long long)m * D + 2 * pp + k;
+      if (MODE == kPolyNcoExact) {
+        const unsigned long long phase = (P.ncoFirst + s) * P.ncoStep;
+        const float a = (float)(int)(unsigned)(phase >> 32) * 4.656612873077392578125e-10f;
+        sincospif(a, &sn[k], &cs[k]);
+      } else {
+        const unsigned idx = P.ncoFirst32 + (unsigned)s;  // ref: src/adjustFrequency.cu:23,35-50; src/fm.cu:43-47
+        const float period = __frcp_rn(P.ncoF);
+        const float tt = __fdiv_rn(fmodf(__uint2float_rn(idx), P.ncoFs), P.ncoFs);
+        const float u = fmodf(tt, period);
+        sincospif(u * 2.0f, &sn[k], &cs[k]);
+      }
+    }
+    float4 r;
+    r.x = __fmaf_rn(v.x, cs[0], -__fmul_rn(v.y, sn[0]));
+    r.y = __fmaf_rn(v.x, sn[0], __fmul_rn(v.y, cs[0]));
+    r.z = __fmaf_rn(v.z, cs[1], -__fmul_rn(v.w, sn[1]));
+    r.w = __fmaf_rn(v.z, sn[1], __fmul_rn(v.w, cs[1]));
+    *q = r;
+  }
+}
+
+// MODE: kPolyFC / kPolyNcoExact / kPolyNcoLiteral.  TG threads own 8 outputs each (tile = 8*TG outputs); PSPLIT
+// thread groups split the branch pairs.  DT: compile-time decimation (row size, swizzle and plane pitch become
+// immediates; needs Jpad <= kTmaJpadCap) or 0 for run-time geometry.  Two window buffers: tile k+1 is in flight
+// while tile k is filtered.
+template <int MODE, int TG, int PSPLIT, int DT, int MINB>
+__global__ void __launch_bounds__(TG* PSPLIT, MINB)
+    firTmaKernel(const __grid_constant__ CUtensorMap map, const TmaParams P) {
+  constexpr unsigned NT = TG * PSPLIT;
+  constexpr unsigned BOUT = kTmaR * TG;
+  extern __shared__ __align__(16) unsigned char smemRaw[];
+  __shared__ __align__(8) unsigned long long fullBar[2];
+  const unsigned D = DT ? (unsigned)DT : P.D;
+  const unsigned rowBytes = 8u * D;
+  const unsigned planeBytes = DT ? tmaPlaneRows(TG, kTmaJpadCap, DT ? DT : 2) * 8u * (unsigned)DT : P.planeBytes;
+  const unsigned bufBytes = 8u * planeBytes;
+  // the swizzle patterns are functions of absolute shared-memory address bits: align the buffers to 1024 bytes
+  unsigned char* bufBase = smemRaw + ((1024u - (smemU32(smemRaw) & 1023u)) & 1023u);  // 2 x bufBytes
+  float4* scratch = reinterpret_cast<float4*>(bufBase + 2u * bufBytes);  // 2 x (PSPLIT-1) x TG x 64 B of partial sums
+  float* hs = reinterpret_cast<float*>(scratch + 2u * (PSPLIT - 1) * (kTmaR / 2) * TG);  // [D/2][Jpad][2] (+32 zeros)
+
+  const unsigned tid = threadIdx.x;
+  const unsigned grp = tid / TG;
+  const unsigned t = tid - grp * TG;
+  const unsigned numPairs = D >> 1;
+  const unsigned ppBegin = (grp * numPairs) / PSPLIT;
+  const unsigned ppEnd = ((grp + 1) * numPairs) / PSPLIT;
+  const unsigned rowsStaged = BOUT + P.Jpad;  // rows a tile needs (8 per output block + the taps' reach)
+
+  if (tid == 0) {
+    mbarInit(&fullBar[0], 1);
+    mbarInit(&fullBar[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  // (channel, tile) of this CTA's current and next work item; the grid stride is pre-split on the host so that no
+  // division is needed per tile.
+  unsigned chan = blockIdx.x / P.tilesPerChannel;
+  unsigned tile = blockIdx.x - chan * P.tilesPerChannel;
+  auto advance = [&](unsigned& c, unsigned& tl) {
+    c += P.strideChan;
+    tl += P.strideTile;
+    if (tl >= P.tilesPerChannel) {
+      tl -= P.tilesPerChannel;
+      c += 1;
+    }
+  };
+  // A tile is TMA-fed when every row it stages is visible to the tensor map.
+  auto tileIsFast = [&](unsigned tl) -> bool { return tl * BOUT + rowsStaged <= P.tmaRows; };
+  auto issueTile = [&](unsigned c, unsigned tl, unsigned b) {
+    if (P.dbg & 1u) return;
+    unsigned char* buf = bufBase + b * bufBytes;
+    if (tileIsFast(tl)) {
+      if (tid == 0) {
+        // generic-proxy accesses to this buffer (mix pass, partial-sum scratch) are ordered before the async-proxy
+        // writes of the tensor copy
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        mbarExpectTx(&fullBar[b], bufBytes);
+        tmaLoad4(buf, &map, &fullBar[b], 0, (int)(tl * (BOUT / 8)), 0, (int)c);
+      }
+    } else {
+      tmaStageSlow<NT, DT>(buf, P.x + (size_t)c * P.xStride, (unsigned long long)tl * BOUT * D, rowsStaged, planeBytes, P);
+    }
+  };
+
+  unsigned phaseBits = 0;  // parity of each buffer's mbarrier
+  if (chan < P.numChannels) issueTile(chan, tile, 0);
+  asm volatile("cp.async.commit_group;\n" ::: "memory");
+  unsigned tapsChan = 0xffffffffu;
+
+  for (unsigned it = 0; chan < P.numChannels; it++) {
+    const unsigned b = it & 1u;
+    unsigned char* buf = bufBase + b * bufBytes;
+    const unsigned long long o0 = (unsigned long long)tile * BOUT;
+    unsigned nextChan = chan, nextTile = tile;
+    advance(nextChan, nextTile);
+    if (nextChan < P.numChannels) issueTile(nextChan, nextTile, b ^ 1u);
+    asm volatile("cp.async.commit_group;\n" ::: "memory");
+
+    // taps -> hs2[pp][j] = (h[j*D + 2pp], h[j*D + 2pp + 1]); once per CTA unless the channel's tap set changes
+    const bool tapsReloaded = chan != tapsChan && (tapsChan == 0xffffffffu || P.hStride != 0);
+    if (tapsReloaded) {
+      const float* h = P.h + (size_t)chan * P.hStride;
+      const unsigned nh = D * P.Jpad;
+      for (unsigned i = tid; i < nh + 32u; i += NT) {
+        const unsigned pp = i / (2u * P.Jpad);
+        const unsigned rem = i - pp * 2u * P.Jpad;
+        const unsigned ti = (rem >> 1) * D + 2u * pp + (rem & 1u);
+        hs[i] = (i < nh && ti < P.T) ? __ldg(h + ti) : 0.0f;
+      }
+    }
+    tapsChan = chan;
+
+    // Data-ready: every thread waits on the tile's mbarrier itself (TMA tiles), so no CTA barrier is needed; the
+    // rare cp.async tiles and tap reloads are written by other threads and do need one.
+    const bool fast = tileIsFast(tile);
+    if (!(P.dbg & 1u) && fast) {
+      mbarWait(&fullBar[b], (phaseBits >> b) & 1u);
+      phaseBits ^= 1u << b;
+    }
+    if (!fast || tapsReloaded) {
+      asm volatile("cp.async.wait_group 1;\n" ::: "memory");  // this tile's slow-path copies have landed
+      __syncthreads();
+    }
+    if (MODE == kPolyNcoExact || MODE == kPolyNcoLiteral) {
+      tmaMixWindow<MODE, NT, DT>(buf, o0 * D, rowsStaged, planeBytes, P);
+      __syncthreads();
+    }
+
+    float2 acc[kTmaR];
+#pragma unroll
+    for (int r = 0; r < kTmaR; r++) acc[r] = make_float2(0.0f, 0.0f);
+    const unsigned ppStop = (P.dbg & 2u) ? ppBegin : ppEnd;
+    if (ppBegin < ppStop) {
+      const unsigned nbk = P.Jpad >> 3;  // even, >= 2
+      // address of (plane 0, row group t + c, branch pair pp)
+      auto blockAddr = [&](unsigned pp, unsigned c) -> const unsigned char* {
+        const unsigned mh = t + c;
+        return buf + (mh * rowBytes + ((pp ^ tmaSwizzle<DT>(mh, P)) << 4));
+      };
+      const float* hp = hs + (size_t)ppBegin * 2u * P.Jpad;
+      float hAP[8], hAQ[8], hBP[8], hBQ[8];
+      float4 q[8];
+#pragma unroll
+      for (int k = 0; k < 8; k += 2) {
+        const float4 v = *reinterpret_cast<const float4*>(hp + 2 * k);
+        hAP[k] = v.x, hAQ[k] = v.y, hAP[k + 1] = v.z, hAQ[k + 1] = v.w;
+        const float4 w = *reinterpret_cast<const float4*>(hp + 16 + 2 * k);
+        hBP[k] = w.x, hBQ[k] = w.y, hBP[k + 1] = w.z, hBQ[k + 1] = w.w;
+      }
+      const unsigned char* a0 = blockAddr(ppBegin, 0);
+#pragma unroll
+      for (int e = 0; e < 6; e++) q[e] = *reinterpret_cast<const float4*>(a0 + (unsigned)e * planeBytes);
+      for (unsigned pp = ppBegin; pp < ppStop; pp++) {
+        // block 0: prologue (new = A).  Its old set B already holds tap block 1 (initial load / previous tail).
+        const unsigned char* a1 = blockAddr(pp, 1);
+        firPairBlock<kBlkPrologue, false>(acc, q, hBP, hBQ, hAP, hAQ, a0, a1, planeBytes, hp);
+        const float* tapNext = hp + 32;  // tap block 2
+        unsigned c = 1;
+        for (; c + 2 < nbk; c += 2) {
+          a0 = a1, a1 = blockAddr(pp, c + 1);
+          firPairBlock<kBlkSteady, true>(acc, q, hAP, hAQ, hBP, hBQ, a0, a1, planeBytes, tapNext);
+          a0 = a1, a1 = blockAddr(pp, c + 2);
+          firPairBlock<kBlkSteady, true>(acc, q, hBP, hBQ, hAP, hAQ, a0, a1, planeBytes, tapNext + 16);
+          tapNext += 32;
+        }
+        // last steady block (odd c = nbk-1): old = A, new = B; refills A with tap block nbk = next pair's block 0
+        a0 = a1, a1 = blockAddr(pp, nbk);
+        firPairBlock<kBlkSteady, true>(acc, q, hAP, hAQ, hBP, hBQ, a0, a1, planeBytes, tapNext);
+        // tail block (even): old = B; its sample look-ahead and tap refills already belong to the next pair
+        a0 = a1;
+        a1 = (pp + 1 < ppStop) ? blockAddr(pp + 1, 0) : a0;
+        firPairBlock<kBlkTail, true>(acc, q, hBP, hBQ, hAP, hAQ, a0, a1, planeBytes, tapNext + 16);
+        a0 = a1;
+        hp += 2u * P.Jpad;
+      }
+    }
+
+    // Partial sums of the branch-pair groups go through a small double-buffered scratch area, so ONE barrier per
+    // tile both publishes them and tells thread 0 that this window may be overwritten by the tile after next.
+    if (PSPLIT > 1 && grp > 0) {
+      float4* red = scratch + (size_t)(it & 1u) * (PSPLIT - 1) * (kTmaR / 2) * TG;
+#pragma unroll
+      for (int k = 0; k < kTmaR / 2; k++) {
+        red[((grp - 1) * (kTmaR / 2) + k) * TG + t] =
+            make_float4(acc[2 * k].x, acc[2 * k].y, acc[2 * k + 1].x, acc[2 * k + 1].y);
+      }
+    }
+    __syncthreads();
+    if (grp == 0) {
+      if (PSPLIT > 1) {
+        const float4* red = scratch + (size_t)(it & 1u) * (PSPLIT - 1) * (kTmaR / 2) * TG;
+#pragma unroll
+        for (int g = 1; g < PSPLIT; g++) {
+#pragma unroll
+          for (int k = 0; k < kTmaR / 2; k++) {
+            const float4 v = red[((g - 1) * (kTmaR / 2) + k) * TG + t];
+            acc[2 * k].x += v.x;
+            acc[2 * k].y += v.y;
+            acc[2 * k + 1].x += v.z;
+            acc[2 * k + 1].y += v.w;
+          }
+        }
+      }
+      const unsigned long long ob = o0 + (unsigned long long)t * kTmaR;
+      float2* y = P.y + (size_t)chan * P.yStride;
+      if (P.y16 && ob + kTmaR <= P.nOut) {
+#pragma unroll
+        for (int r = 0; r < kTmaR; r += 2) {
+          *reinterpret_cast<float4*>(y + ob + r) = make_float4(acc[r].x, acc[r].y, acc[r + 1].x, acc[r + 1].y);
+        }
+      } else {
+#pragma unroll
+        for (int r = 0; r < kTmaR; r++) {
+          if (ob + r < P.nOut) y[ob + r] = acc[r];
+        }
+      }
+    }
+    chan = nextChan;
+    tile = nextTile;
+  }
+  asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+}
+
+}  // namespace gsdr_b200

@@ -12,6 +12,7 @@
 #include <mutex>
 
 #include "fir_kernels.cuh"
+#include "fir_tma_kernel.cuh"
 #include "launch.h"
 
 namespace gsdr_b200 {
@@ -125,16 +126,13 @@ static bool polyGeometry(const PolyVariant& v, size_t D, size_t T, PolyGeom* g) 
 
 template <int MODE, int R, int TG, int PSPLIT, int NBUF, int MINB>
 static cudaError_t launchPolyT(PolyParams& P, size_t smem, int dev, int smCount, cudaStream_t stream) noexcept {
-  static std::atomic<unsigned long long> configured{0};  // bit per device
-  static std::atomic<int> occCache[64];                  // CTAs per SM at the max dynamic smem actually used
+  static std::atomic<size_t> configured[64];  // per device: dynamic shared memory the kernel has been opted in to
   auto kernel = firPolyKernel<MODE, R, TG, PSPLIT, NBUF, MINB>;
-  const unsigned long long bit = 1ull << (dev & 63);
-  if (!(configured.load(std::memory_order_acquire) & bit)) {
-    cudaError_t st = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  if (smem > configured[dev & 63].load(std::memory_order_acquire)) {
+    cudaError_t st = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (st != cudaSuccess) return report(st, "cudaFuncSetAttribute(MaxDynamicSharedMemorySize)");
-    configured.fetch_or(bit, std::memory_order_release);
+    configured[dev & 63].store(smem, std::memory_order_release);
   }
-  (void)occCache;
   int perSm = 0;
   cudaError_t st = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, kernel, TG * PSPLIT, smem);
   if (st != cudaSuccess) return report(st, "cudaOccupancyMaxActiveBlocksPerMultiprocessor");
@@ -164,6 +162,7 @@ static int choosePolyVariant(size_t D, size_t T, size_t nOut, int maxSmem, PolyG
   if (forced >= 0 && forced < kNumVariants) {
     return (polyGeometry(kVariants[forced], D, T, geom) && geom->smemBytes <= (size_t)maxSmem) ? forced : -1;
   }
+  if (forced >= kNumVariants) return -1;  // a TMA variant was requested and did not qualify: direct kernel
   (void)nOut;
   static const int order[] = {1, 2};
   const size_t budgets[] = {(size_t)44 * 1024, (size_t)(226 * 1024) / 2, (size_t)maxSmem};
@@ -178,6 +177,229 @@ static int choosePolyVariant(size_t D, size_t T, size_t nOut, int maxSmem, PolyG
     }
   }
   return -1;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// TMA-fed fast path (fir_tma_kernel.cuh)
+// ---------------------------------------------------------------------------------------------------------
+struct TmaVariant {
+  int tg, psplit, minBlocks;
+  int threads() const { return tg * psplit; }
+};
+// X(id, TG, PSPLIT, MINB) — ids continue after the polyphase variants
+#define GSDR_TMA_VARIANTS(X) \
+  X(0, 64, 2, 2)             \
+  X(1, 32, 2, 4)             \
+  X(2, 64, 1, 2)             \
+  X(3, 128, 1, 1)            \
+  X(4, 128, 2, 1)            \
+  X(5, 32, 4, 3)
+
+static constexpr TmaVariant kTmaVariants[] = {
+#define X(id, tg, ps, mb) {tg, ps, mb},
+    GSDR_TMA_VARIANTS(X)
+#undef X
+};
+static constexpr int kNumTmaVariants = (int)(sizeof(kTmaVariants) / sizeof(kTmaVariants[0]));
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encodeTiled() noexcept {
+  static std::once_flag once;
+  static EncodeTiledFn fn = nullptr;
+  std::call_once(once, []() {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess) {
+      fn = (EncodeTiledFn)p;
+    } else {
+      (void)cudaGetLastError();
+    }
+  });
+  return fn;
+}
+
+struct TmaGeom {
+  bool staticD;
+  unsigned Jpad, mhp, planeBytes, swzShift, swzMask;
+  CUtensorMapSwizzle swizzle;
+  size_t smemBytes;
+};
+
+static bool tmaSupportedDecimation(size_t D) noexcept {
+  return D == 2 || D == 4 || D == 6 || D == 8 || D == 10 || D == 14 || D == 16;
+}
+
+// Decimations with a compile-time-geometry instantiation (the BASELINE shapes).
+static bool tmaStaticDecimation(size_t D) noexcept { return D == 4 || D == 8 || D == 10; }
+
+static bool tmaGeometry(const TmaVariant& v, size_t D, size_t T, TmaGeom* g) noexcept {
+  if (!tmaSupportedDecimation(D) || (D / 2) < (size_t)v.psplit) return false;
+  const size_t J = (T + D - 1) / D;
+  const size_t Jpad = (J + 15) / 16 * 16;
+  const size_t G = 8 * D;
+  g->staticD = tmaStaticDecimation(D) && Jpad <= kTmaJpadCap;
+  g->swizzle = CU_TENSOR_MAP_SWIZZLE_NONE;
+  g->swzShift = 0;
+  g->swzMask = 0;
+  if (G == 32) g->swizzle = CU_TENSOR_MAP_SWIZZLE_32B, g->swzShift = 2, g->swzMask = 1;
+  if (G == 64) g->swizzle = CU_TENSOR_MAP_SWIZZLE_64B, g->swzShift = 1, g->swzMask = 3;
+  if (G == 128) g->swizzle = CU_TENSOR_MAP_SWIZZLE_128B, g->swzShift = 0, g->swzMask = 7;
+  // must agree with the kernel's compile-time tmaPlaneRows(TG, kTmaJpadCap, D) when staticD
+  const size_t mhp = tmaPlaneRows((unsigned)v.tg, (unsigned)(g->staticD ? kTmaJpadCap : Jpad), (unsigned)D);
+  if (mhp > 256) return false;  // TMA box dimension limit
+  g->Jpad = (unsigned)Jpad;
+  g->mhp = (unsigned)mhp;
+  g->planeBytes = (unsigned)(mhp * G);
+  g->smemBytes = 1024 + 2 * 8 * (size_t)g->planeBytes + 2 * (size_t)(v.psplit - 1) * v.tg * 64 + (D * Jpad + 32) * 4;
+  return true;
+}
+
+template <int MODE, int TG, int PSPLIT, int DT, int MINB>
+static cudaError_t launchTmaT(const CUtensorMap& map, TmaParams& P, size_t smem, int dev, int smCount,
+                              cudaStream_t stream) noexcept {
+  static std::atomic<size_t> configured[64];
+  auto kernel = firTmaKernel<MODE, TG, PSPLIT, DT, MINB>;
+  if (smem > configured[dev & 63].load(std::memory_order_acquire)) {
+    cudaError_t st = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (st != cudaSuccess) return report(st, "cudaFuncSetAttribute(MaxDynamicSharedMemorySize)");
+    configured[dev & 63].store(smem, std::memory_order_release);
+  }
+  int perSm = 0;
+  cudaError_t st = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, kernel, TG * PSPLIT, smem);
+  if (st != cudaSuccess) return report(st, "cudaOccupancyMaxActiveBlocksPerMultiprocessor");
+  if (perSm < 1) return cudaErrorInvalidConfiguration;
+  const unsigned long long resident = (unsigned long long)perSm * (unsigned)smCount;
+  const unsigned grid = (unsigned)(P.totalTiles < resident ? P.totalTiles : resident);
+  P.strideChan = grid / P.tilesPerChannel;
+  P.strideTile = grid % P.tilesPerChannel;
+  void* args[] = {(void*)&map, (void*)&P};
+  return cudaLaunchKernel((const void*)kernel, dim3(grid), dim3(TG * PSPLIT), args, smem, stream);
+}
+
+template <int MODE, int DT>
+static cudaError_t launchTmaModeD(int variant, const CUtensorMap& map, TmaParams& P, size_t smem, int dev,
+                                  int smCount, cudaStream_t stream) noexcept {
+  switch (variant) {
+#define X(id, tg, ps, mb) \
+  case id: return launchTmaT<MODE, tg, ps, DT, mb>(map, P, smem, dev, smCount, stream);
+    GSDR_TMA_VARIANTS(X)
+#undef X
+    default: return cudaErrorInvalidValue;
+  }
+}
+
+template <int MODE>
+static cudaError_t launchTmaMode(int variant, bool staticD, const CUtensorMap& map, TmaParams& P, size_t smem,
+                                 int dev, int smCount, cudaStream_t stream) noexcept {
+  if (staticD) {
+    switch (P.D) {
+      case 4: return launchTmaModeD<MODE, 4>(variant, map, P, smem, dev, smCount, stream);
+      case 8: return launchTmaModeD<MODE, 8>(variant, map, P, smem, dev, smCount, stream);
+      case 10: return launchTmaModeD<MODE, 10>(variant, map, P, smem, dev, smCount, stream);
+      default: break;
+    }
+  }
+  return launchTmaModeD<MODE, 0>(variant, map, P, smem, dev, smCount, stream);
+}
+
+// Returns the TMA variant to use for this call, or -1 when the call does not qualify.
+static int chooseTmaVariant(const FirCall& c, int maxSmem, TmaGeom* geom) noexcept {
+  if (c.type != kFirFC) return -1;
+  if (!tmaSupportedDecimation(c.decimation) || !encodeTiled()) return -1;
+  if ((uintptr_t)c.input % 16 != 0) return -1;                       // TMA needs a 16-byte aligned base
+  if (c.numChannels > 1 && (c.inputStride % 2) != 0) return -1;       // ... and 16-byte strides
+  if (c.numChannels > 0x7fffffffull) return -1;
+  const int forced = gForcedVariant.load(std::memory_order_relaxed);
+  if (forced >= kNumVariants) {
+    const int id = forced - kNumVariants;
+    return (id < kNumTmaVariants && tmaGeometry(kTmaVariants[id], c.decimation, c.tapCount, geom) &&
+            geom->smemBytes <= (size_t)maxSmem) ? id : -1;
+  }
+  if (forced != -1) return -1;
+  static const int order[] = {1, 0};
+  for (int id : order) {
+    TmaGeom g;
+    if (tmaGeometry(kTmaVariants[id], c.decimation, c.tapCount, &g) && g.smemBytes <= (size_t)maxSmem) {
+      *geom = g;
+      return id;
+    }
+  }
+  return -1;
+}
+
+static cudaError_t launchTma(const FirCall& c, int variant, const TmaGeom& geom, int dev, int smCount,
+                             cudaStream_t stream) noexcept {
+  const TmaVariant& v = kTmaVariants[variant];
+  const size_t bout = (size_t)kTmaR * v.tg;
+  const unsigned long long tiles = (c.numOutputs + bout - 1) / bout;
+  const unsigned long long total = tiles * c.numChannels;
+  if (tiles > 0x7fffffffull || total > 0x7fffffffull) return cudaErrorInvalidValue;
+  const size_t D = c.decimation;
+  const unsigned long long nIn = (unsigned long long)(c.numOutputs - 1) * D + c.tapCount;
+  const unsigned long long tmaRows = (nIn / (8 * D)) * 8;  // complete groups of 8 rows only: TMA never reads past nIn
+  if (tmaRows / 8 > 0xffffffffull) return cudaErrorInvalidValue;
+
+  TmaParams P{};
+  P.x = (const float2*)c.input;
+  P.h = (const float*)c.taps;
+  P.y = (float2*)c.output;
+  P.nOut = c.numOutputs;
+  P.nIn = nIn;
+  P.xStride = c.inputStride;
+  P.yStride = c.outputStride;
+  P.hStride = c.tapStride;
+  P.tilesPerChannel = (unsigned)tiles;
+  P.totalTiles = (unsigned)total;
+  P.numChannels = (unsigned)c.numChannels;
+  P.D = (unsigned)D;
+  P.T = (unsigned)c.tapCount;
+  P.Jpad = geom.Jpad;
+  P.rowBytes = (unsigned)(8 * D);
+  P.mhp = geom.mhp;
+  P.planeBytes = geom.planeBytes;
+  P.swzShift = geom.swzShift;
+  P.swzMask = geom.swzMask;
+  P.tmaRows = (unsigned)(tmaRows > 0xffffffffull ? 0xffffffffull : tmaRows);
+  P.y16 = ((uintptr_t)c.output % 16 == 0 && (c.numChannels == 1 || (c.outputStride * 8) % 16 == 0)) ? 1u : 0u;
+  P.dbg = (unsigned)gDebugFlags.load(std::memory_order_relaxed);
+  P.ncoStep = ncoPhaseStep(c.frequencyShift, c.sampleRate);
+  P.ncoFirst = c.firstSampleIndex;
+  P.ncoFirst32 = (uint32_t)fmodf((float)c.firstSampleIndex, c.sampleRate);  // ref: src/fm.cu:202
+  P.ncoFs = c.sampleRate;
+  P.ncoF = c.frequencyShift;
+
+  alignas(64) CUtensorMap map;
+  {
+    // dims: (floats of one row | groups of 8 rows | row within the group | channel); when fewer than 8 rows are
+    // visible every tile takes the cp.async path and the map is never dereferenced (but must still encode).
+    const cuuint64_t gdim[4] = {(cuuint64_t)(2 * D), (cuuint64_t)(tmaRows >= 8 ? tmaRows / 8 : 1), 8,
+                                (cuuint64_t)c.numChannels};
+    const cuuint64_t gstride[3] = {(cuuint64_t)(8 * D * 8), (cuuint64_t)(D * 8),
+                                   (cuuint64_t)(c.numChannels > 1 ? c.inputStride * 8 : 8 * D * 8)};
+    const cuuint32_t box[4] = {(cuuint32_t)(2 * D), (cuuint32_t)geom.mhp, 8, 1};
+    const cuuint32_t estr[4] = {1, 1, 1, 1};
+    const CUresult r = encodeTiled()(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)c.input, gdim, gstride, box,
+                                     estr, CU_TENSOR_MAP_INTERLEAVE_NONE, geom.swizzle,
+                                     CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      std::fprintf(stderr, "gsdr-b200: cuTensorMapEncodeTiled failed with CUresult %d\n", (int)r);
+      return cudaErrorInvalidValue;
+    }
+    if (tmaRows < 8) P.tmaRows = 0;
+  }
+  switch (c.nco) {
+    case kNcoNone:
+      return launchTmaMode<kPolyFC>(variant, geom.staticD, map, P, geom.smemBytes, dev, smCount, stream);
+    case kNcoExact:
+      return launchTmaMode<kPolyNcoExact>(variant, geom.staticD, map, P, geom.smemBytes, dev, smCount, stream);
+    case kNcoLiteral:
+      return launchTmaMode<kPolyNcoLiteral>(variant, geom.staticD, map, P, geom.smemBytes, dev, smCount, stream);
+  }
+  return cudaErrorInvalidValue;
 }
 
 template <class IN_T, class OUT_T, class TAP_T>
@@ -222,6 +444,11 @@ cudaError_t enqueueFir(const FirCall& c, cudaStream_t stream) noexcept {
   const DeviceInfo* info = deviceInfo(dev);
   if (!info || info->status != cudaSuccess) return info ? info->status : cudaErrorInvalidDevice;
 
+  {
+    TmaGeom tg{};
+    const int tv = chooseTmaVariant(c, info->maxSmemOptin, &tg);
+    if (tv >= 0) return launchTma(c, tv, tg, dev, info->smCount, stream);
+  }
   const bool polyType = (c.type == kFirFC || c.type == kFirFF);
   PolyGeom geom{};
   const int variant = polyType ? choosePolyVariant(c.decimation, c.tapCount, c.numOutputs, info->maxSmemOptin, &geom) : -1;
@@ -373,12 +600,13 @@ GSDR_C_LINKAGE uint64_t gsdrNcoPhaseStep(float frequencyShift, float sampleRate)
 // ---- tuning / introspection hooks of <gsdr/b200.h> -------------------------------------------------------
 
 GSDR_C_LINKAGE int gsdrB200SetKernelVariant(int variant) GSDR_NO_EXCEPT {
-  if (variant < -2 || variant >= kNumVariants) return -1;
+  if (variant < -2 || variant >= kNumVariants + kNumTmaVariants) return -1;
   gForcedVariant.store(variant, std::memory_order_relaxed);
   return 0;
 }
 
-GSDR_C_LINKAGE int gsdrB200NumKernelVariants(void) GSDR_NO_EXCEPT { return kNumVariants; }
+GSDR_C_LINKAGE int gsdrB200NumKernelVariants(void) GSDR_NO_EXCEPT { return kNumVariants + kNumTmaVariants; }
+GSDR_C_LINKAGE int gsdrB200NumPolyphaseVariants(void) GSDR_NO_EXCEPT { return kNumVariants; }
 
 GSDR_C_LINKAGE int gsdrB200SetDebugFlags(int flags) GSDR_NO_EXCEPT {
   gDebugFlags.store(flags & 3, std::memory_order_relaxed);
@@ -396,6 +624,28 @@ GSDR_C_LINKAGE int gsdrB200DescribeKernel(int firType, size_t decimation, size_t
   info->variant = -1;
   info->smCount = di->smCount;
   if (tapCount == 0 || numOutputs == 0) return 0;
+  if (firType == kFirFC) {
+    // assumes what the common call has: one channel, 16-byte aligned input
+    FirCall probe;
+    probe.type = kFirFC;
+    probe.decimation = decimation;
+    probe.tapCount = tapCount;
+    probe.numOutputs = numOutputs;
+    TmaGeom tg{};
+    const int tv = chooseTmaVariant(probe, di->maxSmemOptin, &tg);
+    if (tv >= 0) {
+      const size_t bout = (size_t)kTmaR * kTmaVariants[tv].tg;
+      info->variant = kNumVariants + tv;
+      info->outputsPerThread = kTmaR;
+      info->threadsPerBlock = kTmaVariants[tv].threads();
+      info->phaseGroups = kTmaVariants[tv].psplit;
+      info->windowBuffers = 2;
+      info->outputsPerBlock = bout;
+      info->sharedBytesPerBlock = tg.smemBytes;
+      info->numBlocks = (numOutputs + bout - 1) / bout;
+      return 0;
+    }
+  }
   PolyGeom g{};
   const bool polyType = (firType == kFirFC || firType == kFirFF);
   const int v = polyType ? choosePolyVariant(decimation, tapCount, numOutputs, di->maxSmemOptin, &g) : -1;

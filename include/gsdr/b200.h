@@ -162,7 +162,7 @@ GSDR_C_LINKAGE GSDR_PUBLIC cudaError_t gsdrFirFCMultiGpuHost(
 /* ---- kernel selection: introspection and test/tuning hook ---------------------------------------------- */
 
 typedef struct gsdrB200KernelInfo {
-  int variant;          /* polyphase variant id, or -1 for the direct (one output per thread) kernel */
+  int variant;          /* kernel variant id (see gsdrB200NumPolyphaseVariants), or -1 for the direct kernel */
   int outputsPerThread; /* R */
   int threadsPerBlock;
   int phaseGroups;      /* thread groups that split the polyphase branches of a tile (partial sums added on chip) */
@@ -188,6 +188,9 @@ GSDR_C_LINKAGE GSDR_PUBLIC int gsdrB200DescribeKernel(
  */
 GSDR_C_LINKAGE GSDR_PUBLIC int gsdrB200SetKernelVariant(int variant) GSDR_NO_EXCEPT;
 GSDR_C_LINKAGE GSDR_PUBLIC int gsdrB200NumKernelVariants(void) GSDR_NO_EXCEPT;
+/* Variant ids [0, gsdrB200NumPolyphaseVariants()) are the cp.async-staged polyphase kernel (any decimation, FC and
+ * FF); ids from there up to gsdrB200NumKernelVariants() are the TMA-fed kernel (FC, even decimation <= 16). */
+GSDR_C_LINKAGE GSDR_PUBLIC int gsdrB200NumPolyphaseVariants(void) GSDR_NO_EXCEPT;
 /*
  * Measurement hook (results are WRONG while set): bit 0 skips the global->shared window copies, bit 1 skips the
  * FIR loop.  Lets a profiler time the two halves of the kernel separately.  0 restores normal operation.

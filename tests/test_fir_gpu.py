@@ -90,23 +90,56 @@ def test_polyphase_against_oracle(kind, D, T, n_in, cuda_device):
         assert np.abs(y.astype(truth.dtype) - truth).max() <= _tol(taps, x)
 
 
-@pytest.mark.parametrize("variant", [-2] + list(range(12)))
+N_POLY, N_ALL = 12, 18  # polyphase (cp.async) variants, then the TMA-fed variants
+
+
+@pytest.mark.parametrize("variant", [-2] + list(range(N_ALL)))
 @pytest.mark.parametrize("kind", ["ff", "fc"])
 def test_every_kernel_variant(kind, variant, cuda_device):
+    assert (g.num_polyphase_variants(), g.num_kernel_variants()) == (N_POLY, N_ALL)
     D, T, n_in = 8, 255, 200_000
     taps = synth.random_taps(T, 77)  # asymmetric: catches tap-order bugs
     x = synth.tone_plus_noise(5, n_in, seed=32, real=(kind == "ff"))
     n_out = g.fir_num_outputs(n_in, T, D) - 3  # ragged: last tile partly filled, input longer than needed
     g.set_kernel_variant(variant)
     info = g.describe_kernel(0 if kind == "fc" else 1, D, T, n_out)
-    assert info.variant == (variant if variant >= 0 else -1)
-    assert g.num_kernel_variants() == 12
+    tma_only_fc = variant >= N_POLY and kind == "ff"  # the TMA kernel is complex-input only
+    assert info.variant == (variant if variant >= 0 and not tma_only_fc else -1)
     y = _run(kind, D, taps, x, n_out, cuda_device)
     want = oracle.fir(kind, D, taps, x, n_out)
-    if variant == -2:
+    if info.variant == -1:
         assert y.tobytes() == want.tobytes(), "direct kernel must reproduce the reference's accumulation order"
     else:
         assert np.abs(y - want).max() <= _tol(taps, x)
+
+
+@pytest.mark.parametrize("variant", list(range(N_POLY, N_ALL)))
+@pytest.mark.parametrize("D,T", [(2, 33), (4, 127), (6, 100), (8, 255), (10, 255), (14, 29), (16, 500)])
+def test_tma_kernel_decimations_and_swizzle_modes(variant, D, T, cuda_device):
+    """Rows of 16..128 bytes: no swizzle for an odd chunk count (D = 2, 6, 10, 14), 32/64/128-byte swizzle for
+    D = 4, 8, 16.  Sizes chosen so that interior tiles (TMA) and the last tile (cp.async, zero fill) both occur."""
+    n_in = 150_001
+    taps = synth.random_taps(T, 5 + D)
+    x = synth.tone_plus_noise(0, n_in, seed=60 + D)
+    n_out = g.fir_num_outputs(n_in, T, D)
+    g.set_kernel_variant(variant)
+    info = g.describe_kernel(0, D, T, n_out)
+    if info.variant == -1:
+        pytest.skip("variant does not fit this shape")
+    y = _run("fc", D, taps, x, n_out, cuda_device)
+    want = oracle.fir("fc", D, taps, x, n_out, threads=8)
+    assert np.abs(y - want).max() <= _tol(taps, x)
+    # fused NCO on the same kernel
+    dt, dx = torch.from_numpy(taps).to(cuda_device), torch.from_numpy(x).to(cuda_device)
+    dz = torch.zeros(n_out, dtype=torch.complex64, device=cuda_device)
+    g.gsdrAdjustFrequencyFirFC(1.0e6, 123456.0, 2 ** 35 + 9, D, dt, T, dx, dz, n_out, 0, None)
+    torch.cuda.synchronize()
+    n_chk = min(n_out, 3000)
+    wz = oracle.adjust_frequency_fir_fc(oracle.NCO_EXACT, 1.0e6, 123456.0, 2 ** 35 + 9, D, taps, x, n_chk, f64=True)
+    assert np.abs(dz[:n_chk].cpu().numpy() - wz).max() <= _tol(taps, x)
+    tail = oracle.adjust_frequency_fir_fc(oracle.NCO_EXACT, 1.0e6, 123456.0, 2 ** 35 + 9 + (n_out - 500) * D, D, taps,
+                                          x[(n_out - 500) * D:], 500, f64=True)
+    assert np.abs(dz[n_out - 500:].cpu().numpy() - tail).max() <= _tol(taps, x)
 
 
 @pytest.mark.parametrize("kind", ["cc", "cf", "fc", "ff"])
