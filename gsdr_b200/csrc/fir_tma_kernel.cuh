@@ -234,13 +234,64 @@ __device__ __forceinline__ void tmaMixWindow(unsigned char* buf, unsigned long l
   }
 }
 
+// The FIR proper for one thread: outputs 8t..8t+7 of the tile in `buf`, branch pairs [ppBegin, ppStop).
+template <int DT>
+__device__ __forceinline__ void firComputePairs(float2 (&acc)[kTmaR], const unsigned char* buf, const float* hs,
+                                                unsigned t, unsigned ppBegin, unsigned ppStop, unsigned Jpad,
+                                                unsigned rowBytes, unsigned planeBytes, const TmaParams& P) {
+  const unsigned nbk = Jpad >> 3;  // even, >= 2
+  // address of (plane 0, row group t + c, branch pair pp)
+  auto blockAddr = [&](unsigned pp, unsigned c) -> const unsigned char* {
+    const unsigned mh = t + c;
+    return buf + (mh * rowBytes + ((pp ^ tmaSwizzle<DT>(mh, P)) << 4));
+  };
+  const float* hp = hs + (size_t)ppBegin * 2u * Jpad;
+  float hAP[8], hAQ[8], hBP[8], hBQ[8];
+  float4 q[8];
+#pragma unroll
+  for (int k = 0; k < 8; k += 2) {
+    const float4 v = *reinterpret_cast<const float4*>(hp + 2 * k);
+    hAP[k] = v.x, hAQ[k] = v.y, hAP[k + 1] = v.z, hAQ[k + 1] = v.w;
+    const float4 w = *reinterpret_cast<const float4*>(hp + 16 + 2 * k);
+    hBP[k] = w.x, hBQ[k] = w.y, hBP[k + 1] = w.z, hBQ[k + 1] = w.w;
+  }
+  const unsigned char* a0 = blockAddr(ppBegin, 0);
+#pragma unroll
+  for (int e = 0; e < 6; e++) q[e] = *reinterpret_cast<const float4*>(a0 + (unsigned)e * planeBytes);
+#pragma unroll 1  // one copy of the ~600-instruction body: a fully unrolled pair loop overflows the instruction cache
+  for (unsigned pp = ppBegin; pp < ppStop; pp++) {
+    // block 0: prologue (new = A).  Its old set B already holds tap block 1 (initial load / previous tail).
+    const unsigned char* a1 = blockAddr(pp, 1);
+    firPairBlock<kBlkPrologue, false>(acc, q, hBP, hBQ, hAP, hAQ, a0, a1, planeBytes, hp);
+    const float* tapNext = hp + 32;  // tap block 2
+    unsigned c = 1;
+    for (; c + 2 < nbk; c += 2) {
+      a0 = a1, a1 = blockAddr(pp, c + 1);
+      firPairBlock<kBlkSteady, true>(acc, q, hAP, hAQ, hBP, hBQ, a0, a1, planeBytes, tapNext);
+      a0 = a1, a1 = blockAddr(pp, c + 2);
+      firPairBlock<kBlkSteady, true>(acc, q, hBP, hBQ, hAP, hAQ, a0, a1, planeBytes, tapNext + 16);
+      tapNext += 32;
+    }
+    // last steady block (odd c = nbk-1): old = A, new = B; refills A with tap block nbk = next pair's block 0
+    a0 = a1, a1 = blockAddr(pp, nbk);
+    firPairBlock<kBlkSteady, true>(acc, q, hAP, hAQ, hBP, hBQ, a0, a1, planeBytes, tapNext);
+    // tail block (even): old = B; its sample look-ahead and tap refills already belong to the next pair
+    a0 = a1;
+    a1 = (pp + 1 < ppStop) ? blockAddr(pp + 1, 0) : a0;
+    firPairBlock<kBlkTail, true>(acc, q, hBP, hBQ, hAP, hAQ, a0, a1, planeBytes, tapNext + 16);
+    a0 = a1;
+    hp += 2u * Jpad;
+  }
+}
+
 // MODE: kPolyFC / kPolyNcoExact / kPolyNcoLiteral.  TG threads own 8 outputs each (tile = 8*TG outputs); PSPLIT
 // thread groups split the branch pairs.  DT: compile-time decimation (row size, swizzle and plane pitch become
 // immediates; needs Jpad <= kTmaJpadCap) or 0 for run-time geometry.  Two window buffers: tile k+1 is in flight
 // while tile k is filtered.
-template <int MODE, int TG, int PSPLIT, int DT, int MINB>
+template <int MODE, int TG, int PSPLIT, int DT, int NBUF, int MINB>
 __global__ void __launch_bounds__(TG* PSPLIT, MINB)
     firTmaKernel(const __grid_constant__ CUtensorMap map, const TmaParams P) {
+  static_assert(NBUF == 1 || NBUF == 2, "one or two window buffers");
   constexpr unsigned NT = TG * PSPLIT;
   constexpr unsigned BOUT = kTmaR * TG;
   extern __shared__ __align__(16) unsigned char smemRaw[];
@@ -250,8 +301,8 @@ __global__ void __launch_bounds__(TG* PSPLIT, MINB)
   const unsigned planeBytes = DT ? tmaPlaneRows(TG, kTmaJpadCap, DT ? DT : 2) * 8u * (unsigned)DT : P.planeBytes;
   const unsigned bufBytes = 8u * planeBytes;
   // the swizzle patterns are functions of absolute shared-memory address bits: align the buffers to 1024 bytes
-  unsigned char* bufBase = smemRaw + ((1024u - (smemU32(smemRaw) & 1023u)) & 1023u);  // 2 x bufBytes
-  float4* scratch = reinterpret_cast<float4*>(bufBase + 2u * bufBytes);  // 2 x (PSPLIT-1) x TG x 64 B of partial sums
+  unsigned char* bufBase = smemRaw + ((1024u - (smemU32(smemRaw) & 1023u)) & 1023u);  // NBUF x bufBytes
+  float4* scratch = reinterpret_cast<float4*>(bufBase + NBUF * bufBytes);  // 2 x (PSPLIT-1) x TG x 64 B of partial sums
   float* hs = reinterpret_cast<float*>(scratch + 2u * (PSPLIT - 1) * (kTmaR / 2) * TG);  // [D/2][Jpad][2] (+32 zeros)
 
   const unsigned tid = threadIdx.x;
@@ -300,17 +351,23 @@ __global__ void __launch_bounds__(TG* PSPLIT, MINB)
   };
 
   unsigned phaseBits = 0;  // parity of each buffer's mbarrier
-  if (chan < P.numChannels) issueTile(chan, tile, 0);
-  asm volatile("cp.async.commit_group;\n" ::: "memory");
+  if (NBUF == 2) {
+    if (chan < P.numChannels) issueTile(chan, tile, 0);
+    asm volatile("cp.async.commit_group;\n" ::: "memory");
+  }
   unsigned tapsChan = 0xffffffffu;
 
   for (unsigned it = 0; chan < P.numChannels; it++) {
-    const unsigned b = it & 1u;
+    const unsigned b = (NBUF == 2) ? (it & 1u) : 0u;
     unsigned char* buf = bufBase + b * bufBytes;
     const unsigned long long o0 = (unsigned long long)tile * BOUT;
     unsigned nextChan = chan, nextTile = tile;
     advance(nextChan, nextTile);
-    if (nextChan < P.numChannels) issueTile(nextChan, nextTile, b ^ 1u);
+    if (NBUF == 2) {
+      if (nextChan < P.numChannels) issueTile(nextChan, nextTile, b ^ 1u);
+    } else {
+      issueTile(chan, tile, 0);  // single buffer: other resident CTAs compute while this copy is in flight
+    }
     asm volatile("cp.async.commit_group;\n" ::: "memory");
 
     // taps -> hs2[pp][j] = (h[j*D + 2pp], h[j*D + 2pp + 1]); once per CTA unless the channel's tap set changes
@@ -335,7 +392,11 @@ __global__ void __launch_bounds__(TG* PSPLIT, MINB)
       phaseBits ^= 1u << b;
     }
     if (!fast || tapsReloaded) {
-      asm volatile("cp.async.wait_group 1;\n" ::: "memory");  // this tile's slow-path copies have landed
+      if (NBUF == 2) {
+        asm volatile("cp.async.wait_group 1;\n" ::: "memory");  // this tile's slow-path copies have landed
+      } else {
+        asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+      }
       __syncthreads();
     }
     if (MODE == kPolyNcoExact || MODE == kPolyNcoLiteral) {
@@ -347,50 +408,7 @@ __global__ void __launch_bounds__(TG* PSPLIT, MINB)
 #pragma unroll
     for (int r = 0; r < kTmaR; r++) acc[r] = make_float2(0.0f, 0.0f);
     const unsigned ppStop = (P.dbg & 2u) ? ppBegin : ppEnd;
-    if (ppBegin < ppStop) {
-      const unsigned nbk = P.Jpad >> 3;  // even, >= 2
-      // address of (plane 0, row group t + c, branch pair pp)
-      auto blockAddr = [&](unsigned pp, unsigned c) -> const unsigned char* {
-        const unsigned mh = t + c;
-        return buf + (mh * rowBytes + ((pp ^ tmaSwizzle<DT>(mh, P)) << 4));
-      };
-      const float* hp = hs + (size_t)ppBegin * 2u * P.Jpad;
-      float hAP[8], hAQ[8], hBP[8], hBQ[8];
-      float4 q[8];
-#pragma unroll
-      for (int k = 0; k < 8; k += 2) {
-        const float4 v = *reinterpret_cast<const float4*>(hp + 2 * k);
-        hAP[k] = v.x, hAQ[k] = v.y, hAP[k + 1] = v.z, hAQ[k + 1] = v.w;
-        const float4 w = *reinterpret_cast<const float4*>(hp + 16 + 2 * k);
-        hBP[k] = w.x, hBQ[k] = w.y, hBP[k + 1] = w.z, hBQ[k + 1] = w.w;
-      }
-      const unsigned char* a0 = blockAddr(ppBegin, 0);
-#pragma unroll
-      for (int e = 0; e < 6; e++) q[e] = *reinterpret_cast<const float4*>(a0 + (unsigned)e * planeBytes);
-      for (unsigned pp = ppBegin; pp < ppStop; pp++) {
-        // block 0: prologue (new = A).  Its old set B already holds tap block 1 (initial load / previous tail).
-        const unsigned char* a1 = blockAddr(pp, 1);
-        firPairBlock<kBlkPrologue, false>(acc, q, hBP, hBQ, hAP, hAQ, a0, a1, planeBytes, hp);
-        const float* tapNext = hp + 32;  // tap block 2
-        unsigned c = 1;
-        for (; c + 2 < nbk; c += 2) {
-          a0 = a1, a1 = blockAddr(pp, c + 1);
-          firPairBlock<kBlkSteady, true>(acc, q, hAP, hAQ, hBP, hBQ, a0, a1, planeBytes, tapNext);
-          a0 = a1, a1 = blockAddr(pp, c + 2);
-          firPairBlock<kBlkSteady, true>(acc, q, hBP, hBQ, hAP, hAQ, a0, a1, planeBytes, tapNext + 16);
-          tapNext += 32;
-        }
-        // last steady block (odd c = nbk-1): old = A, new = B; refills A with tap block nbk = next pair's block 0
-        a0 = a1, a1 = blockAddr(pp, nbk);
-        firPairBlock<kBlkSteady, true>(acc, q, hAP, hAQ, hBP, hBQ, a0, a1, planeBytes, tapNext);
-        // tail block (even): old = B; its sample look-ahead and tap refills already belong to the next pair
-        a0 = a1;
-        a1 = (pp + 1 < ppStop) ? blockAddr(pp + 1, 0) : a0;
-        firPairBlock<kBlkTail, true>(acc, q, hBP, hBQ, hAP, hAQ, a0, a1, planeBytes, tapNext + 16);
-        a0 = a1;
-        hp += 2u * P.Jpad;
-      }
-    }
+    if (ppBegin < ppStop) firComputePairs<DT>(acc, buf, hs, t, ppBegin, ppStop, P.Jpad, rowBytes, planeBytes, P);
 
     // Partial sums of the branch-pair groups go through a small double-buffered scratch area, so ONE barrier per
     // tile both publishes them and tells thread 0 that this window may be overwritten by the tile after next.

@@ -183,20 +183,24 @@ static int choosePolyVariant(size_t D, size_t T, size_t nOut, int maxSmem, PolyG
 // TMA-fed fast path (fir_tma_kernel.cuh)
 // ---------------------------------------------------------------------------------------------------------
 struct TmaVariant {
-  int tg, psplit, minBlocks;
+  int tg, psplit, nbuf, minBlocks;
   int threads() const { return tg * psplit; }
 };
-// X(id, TG, PSPLIT, MINB) — ids continue after the polyphase variants
+// X(id, TG, PSPLIT, NBUF, MINB) — ids continue after the polyphase variants
 #define GSDR_TMA_VARIANTS(X) \
-  X(0, 64, 2, 2)             \
-  X(1, 32, 2, 4)             \
-  X(2, 64, 1, 2)             \
-  X(3, 128, 1, 1)            \
-  X(4, 128, 2, 1)            \
-  X(5, 32, 4, 3)
+  X(0, 64, 2, 2, 2)          \
+  X(1, 32, 2, 2, 4)          \
+  X(2, 64, 1, 2, 2)          \
+  X(3, 128, 2, 2, 1)         \
+  X(4, 32, 4, 2, 3)          \
+  X(5, 32, 2, 1, 6)          \
+  X(6, 64, 2, 1, 4)          \
+  X(7, 32, 1, 1, 8)          \
+  X(8, 32, 1, 2, 5)          \
+  X(9, 64, 1, 1, 4)
 
 static constexpr TmaVariant kTmaVariants[] = {
-#define X(id, tg, ps, mb) {tg, ps, mb},
+#define X(id, tg, ps, nb, mb) {tg, ps, nb, mb},
     GSDR_TMA_VARIANTS(X)
 #undef X
 };
@@ -254,15 +258,16 @@ static bool tmaGeometry(const TmaVariant& v, size_t D, size_t T, TmaGeom* g) noe
   g->Jpad = (unsigned)Jpad;
   g->mhp = (unsigned)mhp;
   g->planeBytes = (unsigned)(mhp * G);
-  g->smemBytes = 1024 + 2 * 8 * (size_t)g->planeBytes + 2 * (size_t)(v.psplit - 1) * v.tg * 64 + (D * Jpad + 32) * 4;
+  g->smemBytes = 1024 + (size_t)v.nbuf * 8 * (size_t)g->planeBytes + 2 * (size_t)(v.psplit - 1) * v.tg * 64 +
+                 (D * Jpad + 32) * 4;
   return true;
 }
 
-template <int MODE, int TG, int PSPLIT, int DT, int MINB>
+template <int MODE, int TG, int PSPLIT, int DT, int NBUF, int MINB>
 static cudaError_t launchTmaT(const CUtensorMap& map, TmaParams& P, size_t smem, int dev, int smCount,
                               cudaStream_t stream) noexcept {
   static std::atomic<size_t> configured[64];
-  auto kernel = firTmaKernel<MODE, TG, PSPLIT, DT, MINB>;
+  auto kernel = firTmaKernel<MODE, TG, PSPLIT, DT, NBUF, MINB>;
   if (smem > configured[dev & 63].load(std::memory_order_acquire)) {
     cudaError_t st = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (st != cudaSuccess) return report(st, "cudaFuncSetAttribute(MaxDynamicSharedMemorySize)");
@@ -272,6 +277,14 @@ static cudaError_t launchTmaT(const CUtensorMap& map, TmaParams& P, size_t smem,
   cudaError_t st = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, kernel, TG * PSPLIT, smem);
   if (st != cudaSuccess) return report(st, "cudaOccupancyMaxActiveBlocksPerMultiprocessor");
   if (perSm < 1) return cudaErrorInvalidConfiguration;
+  // Warps are pinned to one of the SM's four sub-partitions; with a static tile assignment the kernel runs at the
+  // pace of the fullest one, so keep the resident warp count per SM a multiple of 4 (profiles/r01_notes.md).
+  {
+    const int warpsPerCta = (TG * PSPLIT) / 32;
+    int balanced = perSm;
+    while (balanced > 1 && (balanced * warpsPerCta) % 4 != 0) balanced--;
+    if ((balanced * warpsPerCta) % 4 == 0) perSm = balanced;
+  }
   const unsigned long long resident = (unsigned long long)perSm * (unsigned)smCount;
   const unsigned grid = (unsigned)(P.totalTiles < resident ? P.totalTiles : resident);
   P.strideChan = grid / P.tilesPerChannel;
@@ -284,8 +297,8 @@ template <int MODE, int DT>
 static cudaError_t launchTmaModeD(int variant, const CUtensorMap& map, TmaParams& P, size_t smem, int dev,
                                   int smCount, cudaStream_t stream) noexcept {
   switch (variant) {
-#define X(id, tg, ps, mb) \
-  case id: return launchTmaT<MODE, tg, ps, DT, mb>(map, P, smem, dev, smCount, stream);
+#define X(id, tg, ps, nb, mb) \
+  case id: return launchTmaT<MODE, tg, ps, DT, nb, mb>(map, P, smem, dev, smCount, stream);
     GSDR_TMA_VARIANTS(X)
 #undef X
     default: return cudaErrorInvalidValue;
@@ -639,7 +652,7 @@ GSDR_C_LINKAGE int gsdrB200DescribeKernel(int firType, size_t decimation, size_t
       info->outputsPerThread = kTmaR;
       info->threadsPerBlock = kTmaVariants[tv].threads();
       info->phaseGroups = kTmaVariants[tv].psplit;
-      info->windowBuffers = 2;
+      info->windowBuffers = kTmaVariants[tv].nbuf;
       info->outputsPerBlock = bout;
       info->sharedBytesPerBlock = tg.smemBytes;
       info->numBlocks = (numOutputs + bout - 1) / bout;

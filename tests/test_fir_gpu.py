@@ -90,7 +90,7 @@ def test_polyphase_against_oracle(kind, D, T, n_in, cuda_device):
         assert np.abs(y.astype(truth.dtype) - truth).max() <= _tol(taps, x)
 
 
-N_POLY, N_ALL = 12, 18  # polyphase (cp.async) variants, then the TMA-fed variants
+N_POLY, N_ALL = 12, 22  # polyphase (cp.async) variants, then the TMA-fed variants
 
 
 @pytest.mark.parametrize("variant", [-2] + list(range(N_ALL)))
