@@ -43,8 +43,9 @@ struct TmaParams {
   unsigned strideChan, strideTile;  // gridDim.x split as strideChan * tilesPerChannel + strideTile
   unsigned D, T, Jpad;
   unsigned rowBytes;     // G = 8*D
+  unsigned segBytes;     // min(G, 128): bytes of a row stored contiguously in a plane
   unsigned mhp;          // rows per plane in a buffer (box dim 1)
-  unsigned planeBytes;   // mhp * G, a multiple of 1024
+  unsigned planeBytes;   // mhp * segBytes, a whole number of swizzle periods
   unsigned swzShift;     // address bit the chunk XOR takes its source from, relative to mh: see tmaSwizzle()
   unsigned swzMask;      // 0 (no swizzle), 1, 3 or 7
   unsigned tmaRows;      // rows visible to TMA per channel (multiple of 8); windows reaching past it use cp.async
@@ -60,8 +61,11 @@ constexpr unsigned kTmaJpadCap = 64;  // compile-time-geometry kernels hold up t
 
 // Rows per plane of a window buffer: TG row groups for the outputs + Jpad/8 for the taps' reach, rounded so
 // that a plane is a whole number of swizzle periods (swizzled rows) or of 128-byte TMA units (plain rows).
+// Rows wider than 128 bytes (D > 16, a multiple of 16) are stored as row SEGMENTS of 128 bytes, each segment in
+// its own set of 8 planes and fetched by its own tensor copy.
+__host__ __device__ constexpr unsigned tmaSegBytes(unsigned D) { return 8u * D > 128u ? 128u : 8u * D; }
 __host__ __device__ constexpr unsigned tmaPlaneRows(unsigned tg, unsigned jpad, unsigned D) {
-  const unsigned G = 8u * D;
+  const unsigned G = tmaSegBytes(D);
   const unsigned unit = (G == 32u) ? 256u : (G == 64u) ? 512u : (G == 128u) ? 1024u : 128u;
   unsigned mhp = tg + jpad / 8u;
   while ((mhp * G) % unit) mhp++;
@@ -77,17 +81,28 @@ template <int DT>
 __device__ __forceinline__ unsigned tmaSwizzle(unsigned mh, const TmaParams& P) {
   if (DT == 4) return (mh >> 2) & 1u;
   if (DT == 8) return (mh >> 1) & 3u;
-  if (DT == 16) return mh & 7u;
+  if (DT >= 16 && DT % 16 == 0) return mh & 7u;
   if (DT != 0) return 0u;
   return (mh >> P.swzShift) & P.swzMask;
+}
+
+// byte offset inside a buffer of branch pair pp of row group mh, plane 0
+template <int DT>
+__device__ __forceinline__ unsigned tmaPairOffset(unsigned mh, unsigned pp, unsigned planeBytes, const TmaParams& P) {
+  const unsigned segBytes = DT ? tmaSegBytes(DT ? DT : 2) : P.segBytes;
+  const unsigned pairsPerSeg = segBytes >> 4;
+  unsigned seg = 0, chunk = pp;
+  if (!DT || 8u * DT > 128u) {
+    seg = pp / pairsPerSeg;
+    chunk = pp - seg * pairsPerSeg;
+  }
+  return seg * 8u * planeBytes + mh * segBytes + ((chunk ^ tmaSwizzle<DT>(mh, P)) << 4);
 }
 
 // byte offset inside a buffer of sample (row m, phase p)
 template <int DT>
 __device__ __forceinline__ unsigned tmaSampleOffset(unsigned m, unsigned p, unsigned planeBytes, const TmaParams& P) {
-  const unsigned mh = m >> 3;
-  const unsigned rowBytes = DT ? 8u * DT : P.rowBytes;
-  return (m & 7u) * planeBytes + mh * rowBytes + ((((p >> 1) ^ tmaSwizzle<DT>(mh, P))) << 4) + (p & 1u) * 8u;
+  return (m & 7u) * planeBytes + tmaPairOffset<DT>(m >> 3, p >> 1, planeBytes, P) + (p & 1u) * 8u;
 }
 
 __device__ __forceinline__ unsigned smemU32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -238,12 +253,11 @@ __device__ __forceinline__ void tmaMixWindow(unsigned char* buf, unsigned long l
 template <int DT>
 __device__ __forceinline__ void firComputePairs(float2 (&acc)[kTmaR], const unsigned char* buf, const float* hs,
                                                 unsigned t, unsigned ppBegin, unsigned ppStop, unsigned Jpad,
-                                                unsigned rowBytes, unsigned planeBytes, const TmaParams& P) {
+                                                unsigned planeBytes, const TmaParams& P) {
   const unsigned nbk = Jpad >> 3;  // even, >= 2
   // address of (plane 0, row group t + c, branch pair pp)
   auto blockAddr = [&](unsigned pp, unsigned c) -> const unsigned char* {
-    const unsigned mh = t + c;
-    return buf + (mh * rowBytes + ((pp ^ tmaSwizzle<DT>(mh, P)) << 4));
+    return buf + tmaPairOffset<DT>(t + c, pp, planeBytes, P);
   };
   const float* hp = hs + (size_t)ppBegin * 2u * Jpad;
   float hAP[8], hAQ[8], hBP[8], hBQ[8];
@@ -298,8 +312,10 @@ __global__ void __launch_bounds__(TG* PSPLIT, MINB)
   __shared__ __align__(8) unsigned long long fullBar[2];
   const unsigned D = DT ? (unsigned)DT : P.D;
   const unsigned rowBytes = 8u * D;
-  const unsigned planeBytes = DT ? tmaPlaneRows(TG, kTmaJpadCap, DT ? DT : 2) * 8u * (unsigned)DT : P.planeBytes;
-  const unsigned bufBytes = 8u * planeBytes;
+  const unsigned segBytes = DT ? tmaSegBytes(DT ? DT : 2) : P.segBytes;
+  const unsigned numSegs = rowBytes / segBytes;
+  const unsigned planeBytes = DT ? tmaPlaneRows(TG, kTmaJpadCap, DT ? DT : 2) * segBytes : P.planeBytes;
+  const unsigned bufBytes = numSegs * 8u * planeBytes;
   // the swizzle patterns are functions of absolute shared-memory address bits: align the buffers to 1024 bytes
   unsigned char* bufBase = smemRaw + ((1024u - (smemU32(smemRaw) & 1023u)) & 1023u);  // NBUF x bufBytes
   float4* scratch = reinterpret_cast<float4*>(bufBase + NBUF * bufBytes);  // 2 x (PSPLIT-1) x TG x 64 B of partial sums
@@ -343,7 +359,10 @@ __global__ void __launch_bounds__(TG* PSPLIT, MINB)
         // writes of the tensor copy
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         mbarExpectTx(&fullBar[b], bufBytes);
-        tmaLoad4(buf, &map, &fullBar[b], 0, (int)(tl * (BOUT / 8)), 0, (int)c);
+        for (unsigned sg = 0; sg < numSegs; sg++) {
+          tmaLoad4(buf + sg * 8u * planeBytes, &map, &fullBar[b], (int)(sg * (segBytes / 4u)), (int)(tl * (BOUT / 8)), 0,
+                   (int)c);
+        }
       }
     } else {
       tmaStageSlow<NT, DT>(buf, P.x + (size_t)c * P.xStride, (unsigned long long)tl * BOUT * D, rowsStaged, planeBytes, P);
@@ -408,7 +427,7 @@ __global__ void __launch_bounds__(TG* PSPLIT, MINB)
 #pragma unroll
     for (int r = 0; r < kTmaR; r++) acc[r] = make_float2(0.0f, 0.0f);
     const unsigned ppStop = (P.dbg & 2u) ? ppBegin : ppEnd;
-    if (ppBegin < ppStop) firComputePairs<DT>(acc, buf, hs, t, ppBegin, ppStop, P.Jpad, rowBytes, planeBytes, P);
+    if (ppBegin < ppStop) firComputePairs<DT>(acc, buf, hs, t, ppBegin, ppStop, P.Jpad, planeBytes, P);
 
     // Partial sums of the branch-pair groups go through a small double-buffered scratch area, so ONE barrier per
     // tile both publishes them and tells thread 0 that this window may be overwritten by the tile after next.

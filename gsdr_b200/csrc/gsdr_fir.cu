@@ -197,7 +197,9 @@ struct TmaVariant {
   X(6, 64, 2, 1, 4)          \
   X(7, 32, 1, 1, 8)          \
   X(8, 32, 1, 2, 5)          \
-  X(9, 64, 1, 1, 4)
+  X(9, 64, 1, 1, 4)          \
+  X(10, 32, 4, 1, 2)         \
+  X(11, 32, 8, 1, 1)
 
 static constexpr TmaVariant kTmaVariants[] = {
 #define X(id, tg, ps, nb, mb) {tg, ps, nb, mb},
@@ -234,17 +236,19 @@ struct TmaGeom {
 };
 
 static bool tmaSupportedDecimation(size_t D) noexcept {
-  return D == 2 || D == 4 || D == 6 || D == 8 || D == 10 || D == 14 || D == 16;
+  // rows of 16..128 bytes whose bank pattern is conflict free (odd chunk count, or a TMA swizzle mode exists),
+  // and wider rows that split into 128-byte segments
+  return D == 2 || D == 4 || D == 6 || D == 8 || D == 10 || D == 14 || (D >= 16 && D % 16 == 0 && D <= 256);
 }
 
 // Decimations with a compile-time-geometry instantiation (the BASELINE shapes).
-static bool tmaStaticDecimation(size_t D) noexcept { return D == 4 || D == 8 || D == 10; }
+static bool tmaStaticDecimation(size_t D) noexcept { return D == 4 || D == 8 || D == 10 || D == 32; }
 
 static bool tmaGeometry(const TmaVariant& v, size_t D, size_t T, TmaGeom* g) noexcept {
   if (!tmaSupportedDecimation(D) || (D / 2) < (size_t)v.psplit) return false;
   const size_t J = (T + D - 1) / D;
   const size_t Jpad = (J + 15) / 16 * 16;
-  const size_t G = 8 * D;
+  const size_t G = tmaSegBytes((unsigned)D);
   g->staticD = tmaStaticDecimation(D) && Jpad <= kTmaJpadCap;
   g->swizzle = CU_TENSOR_MAP_SWIZZLE_NONE;
   g->swzShift = 0;
@@ -258,8 +262,8 @@ static bool tmaGeometry(const TmaVariant& v, size_t D, size_t T, TmaGeom* g) noe
   g->Jpad = (unsigned)Jpad;
   g->mhp = (unsigned)mhp;
   g->planeBytes = (unsigned)(mhp * G);
-  g->smemBytes = 1024 + (size_t)v.nbuf * 8 * (size_t)g->planeBytes + 2 * (size_t)(v.psplit - 1) * v.tg * 64 +
-                 (D * Jpad + 32) * 4;
+  g->smemBytes = 1024 + (size_t)v.nbuf * (8 * D / G) * 8 * (size_t)g->planeBytes +
+                 2 * (size_t)(v.psplit - 1) * v.tg * 64 + (D * Jpad + 32) * 4;
   return true;
 }
 
@@ -313,6 +317,7 @@ static cudaError_t launchTmaMode(int variant, bool staticD, const CUtensorMap& m
       case 4: return launchTmaModeD<MODE, 4>(variant, map, P, smem, dev, smCount, stream);
       case 8: return launchTmaModeD<MODE, 8>(variant, map, P, smem, dev, smCount, stream);
       case 10: return launchTmaModeD<MODE, 10>(variant, map, P, smem, dev, smCount, stream);
+      case 32: return launchTmaModeD<MODE, 32>(variant, map, P, smem, dev, smCount, stream);
       default: break;
     }
   }
@@ -333,8 +338,15 @@ static int chooseTmaVariant(const FirCall& c, int maxSmem, TmaGeom* geom) noexce
             geom->smemBytes <= (size_t)maxSmem) ? id : -1;
   }
   if (forced != -1) return -1;
-  static const int order[] = {1, 0};
-  for (int id : order) {
+  // hand-tuned preference (tools/sweep.py): narrow rows -> 32 outputs-threads x 2 branch groups, double buffered;
+  // wide rows (many branch pairs, big windows) -> 4 or 8 branch groups on a single buffer, 2 CTAs per SM
+  static const int orderNarrow[] = {1, 5, 0};
+  static const int orderWide[] = {4, 10, 11, 1};
+  const bool wide = c.decimation > 16;
+  const int* order = wide ? orderWide : orderNarrow;
+  const int orderLen = wide ? 4 : 3;
+  for (int k = 0; k < orderLen; k++) {
+    const int id = order[k];
     TmaGeom g;
     if (tmaGeometry(kTmaVariants[id], c.decimation, c.tapCount, &g) && g.smemBytes <= (size_t)maxSmem) {
       *geom = g;
@@ -372,6 +384,7 @@ static cudaError_t launchTma(const FirCall& c, int variant, const TmaGeom& geom,
   P.T = (unsigned)c.tapCount;
   P.Jpad = geom.Jpad;
   P.rowBytes = (unsigned)(8 * D);
+  P.segBytes = tmaSegBytes((unsigned)D);
   P.mhp = geom.mhp;
   P.planeBytes = geom.planeBytes;
   P.swzShift = geom.swzShift;
@@ -393,7 +406,7 @@ static cudaError_t launchTma(const FirCall& c, int variant, const TmaGeom& geom,
                                 (cuuint64_t)c.numChannels};
     const cuuint64_t gstride[3] = {(cuuint64_t)(8 * D * 8), (cuuint64_t)(D * 8),
                                    (cuuint64_t)(c.numChannels > 1 ? c.inputStride * 8 : 8 * D * 8)};
-    const cuuint32_t box[4] = {(cuuint32_t)(2 * D), (cuuint32_t)geom.mhp, 8, 1};
+    const cuuint32_t box[4] = {(cuuint32_t)(tmaSegBytes((unsigned)D) / 4), (cuuint32_t)geom.mhp, 8, 1};
     const cuuint32_t estr[4] = {1, 1, 1, 1};
     const CUresult r = encodeTiled()(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)c.input, gdim, gstride, box,
                                      estr, CU_TENSOR_MAP_INTERLEAVE_NONE, geom.swizzle,

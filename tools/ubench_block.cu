@@ -64,7 +64,7 @@ __global__ void __launch_bounds__(128) k_tile(float* out, int iters, TmaParams P
     float2 acc[8];
 #pragma unroll
     for (int r = 0; r < 8; r++) acc[r] = make_float2(0.f, 0.f);
-    firComputePairs<8>(acc, sm, hs, threadIdx.x, 0, 4, 32, 64, planeBytes, P);
+    firComputePairs<8>(acc, sm, hs, threadIdx.x, 0, 4, 32, planeBytes, P);
 #pragma unroll
     for (int i = 0; i < 8; i++) s += acc[i].x + acc[i].y;
   }
