@@ -44,6 +44,10 @@ WORKLOADS = {
                  desc="complex FIR, 255 real taps, decimation 8, 64Mi cuComplex samples per GPU (BASELINE config 2)"),
     "cfg3": dict(D=32, T=1023, n_in=1 << 28, nco=True,
                  desc="fused NCO mix + 1023-tap decimate-by-32, 256Mi samples per GPU (BASELINE config 3)"),
+    "cfg3-nomix": dict(D=32, T=1023, n_in=1 << 28, nco=False,
+                       desc="1023-tap decimate-by-32 complex FIR without the NCO, 256Mi samples per GPU"),
+    "cfg5s1": dict(D=10, T=255, n_in=1 << 28, nco=True,
+                   desc="fused NCO mix + 255-tap decimate-by-10 (BASELINE config 5 stage 1 shape), 256Mi samples per GPU"),
 }
 PAPER_FP32_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12  # 74.45
 
@@ -353,7 +357,7 @@ def main() -> None:
     if not args.no_cpu and world == 1:
         cpu = _cpu_baseline(D, T, taps, n_in_gpu)
 
-    info = g.describe_kernel(0, D, T, sh.numOutputs, local) if args.impl == "ours" else None
+    info = g.describe_kernel(4 if wl["nco"] else 0, D, T, sh.numOutputs, local) if args.impl == "ours" else None
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",

@@ -212,40 +212,83 @@ __device__ __forceinline__ void tmaStageSlow(unsigned char* buf, const float2* s
   }
 }
 
+// Phasor of absolute sample n for the exact NCO: top 32 bits of (n * step mod 2^64) -> angle / pi in [-1, 1).
+__device__ __forceinline__ float2 ncoExactPhasor(unsigned long long n, unsigned long long step) {
+  const unsigned long long phase = n * step;
+  const float a = (float)(int)(unsigned)(phase >> 32) * 4.656612873077392578125e-10f;
+  float sn, cs;
+  sincospif(a, &sn, &cs);
+  return make_float2(cs, sn);
+}
+__device__ __forceinline__ float2 cmulf(float2 a, float2 b) {
+  return make_float2(__fmaf_rn(a.x, b.x, -__fmul_rn(a.y, b.y)), __fmaf_rn(a.x, b.y, __fmul_rn(a.y, b.x)));
+}
+
 // In-place NCO mix of a landed window (all threads).  Element (m, p) is input sample in0 + m*D + p.
+//
+// Exact mode: phasor(row m, phase p) = A[m] * R[p] with A[m] = exp(j*phase(first sample of row m)) evaluated by
+// sincospi from the exact 64-bit phase (one per row, pass 1) and R[p] = exp(j*p*step) a per-CTA table.  Two
+// roundings per phasor, no recurrence chain (every element is independent: full ILP), and a pure function of the
+// absolute sample index given the row alignment — which is identical for sharded and unsharded runs (shards and
+// tiles start on multiples of D), so time shards reproduce the unsharded bits.  Work items are (branch pair,
+// plane, row group) with consecutive lanes on consecutive row groups, like the FIR reader (conflict free).
+// Literal mode (parity with the reference only): the reference's arithmetic per sample.
 template <int MODE, int NT, int DT>
 __device__ __forceinline__ void tmaMixWindow(unsigned char* buf, unsigned long long in0, unsigned rows,
-                                             unsigned planeBytes, const TmaParams& P) {
+                                             unsigned planeBytes, float2* ncoA, const float2* ncoR,
+                                             const TmaParams& P) {
   const unsigned D = DT ? (unsigned)DT : P.D;
   const unsigned pairsPerRow = D >> 1;
-  const unsigned total = rows * pairsPerRow;
-  for (unsigned e = threadIdx.x; e < total; e += NT) {
-    const unsigned m = e / pairsPerRow;
-    const unsigned pp = e - m * pairsPerRow;
-    float4* q = reinterpret_cast<float4*>(buf + tmaSampleOffset<DT>(m, 2 * pp, planeBytes, P));
-    float4 v = *q;
-    float sn[2], cs[2];
+  if (MODE == kPolyNcoExact) {
+    const unsigned mhCount = rows >> 3;  // rows is a multiple of 8
+    // pass 1: row anchors, stored [ml][mh] so that pass 2 reads them with consecutive lanes
+    for (unsigned m = threadIdx.x; m < rows; m += NT) {
+      ncoA[(m & 7u) * mhCount + (m >> 3)] = ncoExactPhasor(P.ncoFirst + in0 + (unsigned long long)m * D, P.ncoStep);
+    }
+    __syncthreads();
+    const unsigned total = pairsPerRow * rows;
+    unsigned g = threadIdx.x / mhCount;  // g = pp * 8 + ml
+    unsigned mh = threadIdx.x - g * mhCount;
+    const unsigned dg = NT / mhCount, dmh = NT - dg * mhCount;
+    for (unsigned e = threadIdx.x; e < total; e += NT) {
+      const unsigned pp = g >> 3, ml = g & 7u;
+      const float2 an = ncoA[ml * mhCount + mh];
+      const float4 rr = *reinterpret_cast<const float4*>(ncoR + 2u * pp);
+      float4* q = reinterpret_cast<float4*>(buf + ml * planeBytes + tmaPairOffset<DT>(mh, pp, planeBytes, P));
+      const float4 v = *q;
+      const float2 w0 = cmulf(an, make_float2(rr.x, rr.y));
+      const float2 w1 = cmulf(an, make_float2(rr.z, rr.w));
+      const float2 a = cmulf(make_float2(v.x, v.y), w0);
+      const float2 c = cmulf(make_float2(v.z, v.w), w1);
+      *q = make_float4(a.x, a.y, c.x, c.y);
+      g += dg;
+      mh += dmh;
+      if (mh >= mhCount) {
+        mh -= mhCount;
+        g += 1;
+      }
+    }
+  } else {
+    const unsigned total = rows * pairsPerRow;
+    for (unsigned e = threadIdx.x; e < total; e += NT) {
+      const unsigned m = e / pairsPerRow;
+      const unsigned pp = e - m * pairsPerRow;
+      float4* q = reinterpret_cast<float4*>(buf + tmaSampleOffset<DT>(m, 2 * pp, planeBytes, P));
+      const float4 v = *q;
+      float2 w[2];
 #pragma unroll
-    for (int k = 0; k < 2; k++) {
-      const unsigned long long s = in0 + (unsigned long long)m * D + 2 * pp + k;
-      if (MODE == kPolyNcoExact) {
-        const unsigned long long phase = (P.ncoFirst + s) * P.ncoStep;
-        const float a = (float)(int)(unsigned)(phase >> 32) * 4.656612873077392578125e-10f;
-        sincospif(a, &sn[k], &cs[k]);
-      } else {
+      for (int k = 0; k < 2; k++) {
+        const unsigned long long s = in0 + (unsigned long long)m * D + 2 * pp + k;
         const unsigned idx = P.ncoFirst32 + (unsigned)s;  // ref: src/adjustFrequency.cu:23,35-50; src/fm.cu:43-47
         const float period = __frcp_rn(P.ncoF);
         const float tt = __fdiv_rn(fmodf(__uint2float_rn(idx), P.ncoFs), P.ncoFs);
         const float u = fmodf(tt, period);
-        sincospif(u * 2.0f, &sn[k], &cs[k]);
+        sincospif(u * 2.0f, &w[k].y, &w[k].x);
       }
+      const float2 a = cmulf(make_float2(v.x, v.y), w[0]);
+      const float2 c = cmulf(make_float2(v.z, v.w), w[1]);
+      *q = make_float4(a.x, a.y, c.x, c.y);
     }
-    float4 r;
-    r.x = __fmaf_rn(v.x, cs[0], -__fmul_rn(v.y, sn[0]));
-    r.y = __fmaf_rn(v.x, sn[0], __fmul_rn(v.y, cs[0]));
-    r.z = __fmaf_rn(v.z, cs[1], -__fmul_rn(v.w, sn[1]));
-    r.w = __fmaf_rn(v.z, sn[1], __fmul_rn(v.w, cs[1]));
-    *q = r;
   }
 }
 
@@ -320,6 +363,9 @@ __global__ void __launch_bounds__(TG* PSPLIT, MINB)
   unsigned char* bufBase = smemRaw + ((1024u - (smemU32(smemRaw) & 1023u)) & 1023u);  // NBUF x bufBytes
   float4* scratch = reinterpret_cast<float4*>(bufBase + NBUF * bufBytes);  // 2 x (PSPLIT-1) x TG x 64 B of partial sums
   float* hs = reinterpret_cast<float*>(scratch + 2u * (PSPLIT - 1) * (kTmaR / 2) * TG);  // [D/2][Jpad][2] (+32 zeros)
+  // exact NCO only: per-row anchors of the current window and the per-CTA table exp(j*p*step), p < D
+  float2* ncoA = reinterpret_cast<float2*>(hs + (size_t)(DT ? DT : P.D) * P.Jpad + 32u);
+  float2* ncoR = ncoA + (BOUT + P.Jpad);
 
   const unsigned tid = threadIdx.x;
   const unsigned grp = tid / TG;
@@ -333,6 +379,9 @@ __global__ void __launch_bounds__(TG* PSPLIT, MINB)
     mbarInit(&fullBar[0], 1);
     mbarInit(&fullBar[1], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (MODE == kPolyNcoExact) {
+    for (unsigned p = tid; p < D; p += NT) ncoR[p] = ncoExactPhasor((unsigned long long)p, P.ncoStep);
   }
   __syncthreads();
 
@@ -419,7 +468,7 @@ __global__ void __launch_bounds__(TG* PSPLIT, MINB)
       __syncthreads();
     }
     if (MODE == kPolyNcoExact || MODE == kPolyNcoLiteral) {
-      tmaMixWindow<MODE, NT, DT>(buf, o0 * D, rowsStaged, planeBytes, P);
+      tmaMixWindow<MODE, NT, DT>(buf, o0 * D, rowsStaged, planeBytes, ncoA, ncoR, P);
       __syncthreads();
     }
 

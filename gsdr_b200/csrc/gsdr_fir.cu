@@ -263,7 +263,8 @@ static bool tmaGeometry(const TmaVariant& v, size_t D, size_t T, TmaGeom* g) noe
   g->mhp = (unsigned)mhp;
   g->planeBytes = (unsigned)(mhp * G);
   g->smemBytes = 1024 + (size_t)v.nbuf * (8 * D / G) * 8 * (size_t)g->planeBytes +
-                 2 * (size_t)(v.psplit - 1) * v.tg * 64 + (D * Jpad + 32) * 4;
+                 2 * (size_t)(v.psplit - 1) * v.tg * 64 + (D * Jpad + 32) * 4 +
+                 ((size_t)kTmaR * v.tg + Jpad + D) * 8;  // NCO row anchors + rotation table
   return true;
 }
 
@@ -340,11 +341,21 @@ static int chooseTmaVariant(const FirCall& c, int maxSmem, TmaGeom* geom) noexce
   if (forced != -1) return -1;
   // hand-tuned preference (tools/sweep.py): narrow rows -> 32 outputs-threads x 2 branch groups, double buffered;
   // wide rows (many branch pairs, big windows) -> 4 or 8 branch groups on a single buffer, 2 CTAs per SM
-  static const int orderNarrow[] = {1, 5, 0};
+  // With the fused NCO every CTA alternates a mix pass (latency bound) and the FIR: more, single-buffered CTAs per
+  // SM overlap one CTA's mix with another's FIR better than double buffering does.
+  // ids: 1 = (32 threads x 2 groups, double buffered), 8 = (32 x 1, double buffered), 5 / 10 = single-buffered
+  // 2 / 4 groups, 4 = (32 x 4, double buffered), 11 = (32 x 8, single buffered)
+  static const int orderEvenPairs[] = {1, 8, 5, 0};   // D = 8, 16: the branch pairs split evenly over 2 groups
+  static const int orderOddPairs[] = {8, 1, 5, 0};    // D = 2, 4, 6, 10, 14: one group keeps all pairs
   static const int orderWide[] = {4, 10, 11, 1};
+  static const int orderNarrowNco[] = {10, 5, 1, 8};
+  static const int orderWideNco[] = {10, 11, 4, 1};
   const bool wide = c.decimation > 16;
-  const int* order = wide ? orderWide : orderNarrow;
-  const int orderLen = wide ? 4 : 3;
+  const bool nco = c.nco != kNcoNone;
+  const bool evenPairs = ((c.decimation / 2) % 2 == 0) && c.decimation >= 8;
+  const int* order = wide ? (nco ? orderWideNco : orderWide)
+                          : (nco ? orderNarrowNco : (evenPairs ? orderEvenPairs : orderOddPairs));
+  const int orderLen = 4;
   for (int k = 0; k < orderLen; k++) {
     const int id = order[k];
     TmaGeom g;
@@ -650,10 +661,11 @@ GSDR_C_LINKAGE int gsdrB200DescribeKernel(int firType, size_t decimation, size_t
   info->variant = -1;
   info->smCount = di->smCount;
   if (tapCount == 0 || numOutputs == 0) return 0;
-  if (firType == kFirFC) {
+  if (firType == kFirFC || firType == 4) {
     // assumes what the common call has: one channel, 16-byte aligned input
     FirCall probe;
     probe.type = kFirFC;
+    probe.nco = (firType == 4) ? kNcoExact : kNcoNone;
     probe.decimation = decimation;
     probe.tapCount = tapCount;
     probe.numOutputs = numOutputs;
@@ -673,7 +685,7 @@ GSDR_C_LINKAGE int gsdrB200DescribeKernel(int firType, size_t decimation, size_t
     }
   }
   PolyGeom g{};
-  const bool polyType = (firType == kFirFC || firType == kFirFF);
+  const bool polyType = (firType == kFirFC || firType == kFirFF || firType == 4);
   const int v = polyType ? choosePolyVariant(decimation, tapCount, numOutputs, di->maxSmemOptin, &g) : -1;
   info->variant = v;
   if (v >= 0) {

@@ -173,7 +173,8 @@ typedef struct gsdrB200KernelInfo {
   size_t numBlocks;
 } gsdrB200KernelInfo;
 
-/* firType: 0 = FC, 1 = FF, 2 = CC, 3 = CF.  Reports the kernel a call of that shape would launch. */
+/* firType: 0 = FC, 1 = FF, 2 = CC, 3 = CF, 4 = FC with the fused NCO.  Reports the kernel a call of that shape
+ * (one channel, 16-byte aligned pointers) would launch. */
 GSDR_C_LINKAGE GSDR_PUBLIC int gsdrB200DescribeKernel(
     int firType,
     size_t decimation,
