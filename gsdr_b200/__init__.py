@@ -18,6 +18,9 @@ from .api import (  # noqa: F401
     gsdrFirFCBatched,
     gsdrFirFF,
     gsdrFirFFBatched,
+    gsdrFmDemod,
+    gsdrQuadAmDemod,
+    gsdrQuadFmDemod,
     nco_phase_step,
     set_kernel_variant,
     num_kernel_variants,

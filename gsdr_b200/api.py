@@ -81,6 +81,23 @@ gsdrAdjustFrequencyFirFC = _nco("gsdrAdjustFrequencyFirFC")
 gsdrAdjustFrequencyFirFCLiteral = _nco("gsdrAdjustFrequencyFirFCLiteral")
 
 
+def gsdrQuadFmDemod(input, output, gain, numOutputElements, cudaDevice=0, cudaStream=None):
+    _check(lib.gsdrQuadFmDemod(_ptr(input), _ptr(output), gain, numOutputElements, cudaDevice, _stream(cudaStream)),
+           "gsdrQuadFmDemod")
+
+
+def gsdrQuadAmDemod(input, output, numOutputElements, cudaDevice=0, cudaStream=None):
+    _check(lib.gsdrQuadAmDemod(_ptr(input), _ptr(output), numOutputElements, cudaDevice, _stream(cudaStream)),
+           "gsdrQuadAmDemod")
+
+
+def gsdrFmDemod(rfSampleRate, tuningFrequency, channelFrequency, frequencyDeviation, decimation, firstSampleIndex,
+                lowPassTaps, numLowPassTaps, input, output, numOutputs, cudaDevice=0, cudaStream=None):
+    _check(lib.gsdrFmDemod(rfSampleRate, tuningFrequency, channelFrequency, frequencyDeviation, decimation,
+                           firstSampleIndex, _ptr(lowPassTaps), numLowPassTaps, _ptr(input), _ptr(output), numOutputs,
+                           cudaDevice, _stream(cudaStream)), "gsdrFmDemod")
+
+
 def _batched(name):
     fn = getattr(lib, name)
 

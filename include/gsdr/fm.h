@@ -1,0 +1,48 @@
+/*
+ * gsdr/fm.h — FM receive stage: NCO mix-down, real-tap low-pass, decimate, quadrature demodulate.  C ABI.
+ * Same symbol, argument order and types as the reference's include/gsdr/fm.h (ref: include/gsdr/fm.h:42-55);
+ * replaces ref: src/fm.cu:21-69 (k_Fm) and :181-218 (gsdrFmDemod).
+ *
+ *   lp[n]     = sum_{i<numLowPassTaps} input[n*D + i] * nco(firstSampleIndex + n*D + i) * lowPassTaps[i]
+ *   output[n] = gain * atan2f(Im(m), Re(m)),  m = lp[n+1] * conj(lp[n]),  n in [0, numOutputs)
+ *   gain = rfSampleRate / (2*pi*frequencyDeviation)            (ref: src/fm.cu:203)
+ *   nco  = exp(j*2*pi*(tuningFrequency - channelFrequency)*k/rfSampleRate)   (frequencyShift, ref: src/fm.cu:204)
+ *
+ * This is the stage as the reference documents it.  The reference's own kernel cannot serve as an oracle here:
+ * k_AdjustFrequency returns no value (ref: src/adjustFrequency.cu:55-56), the grid is short by 1/32 of the
+ * outputs and lanes exit before a full-mask shuffle (ref: src/fm.cu:34-36,58-64).  The NCO is the exact
+ * 64-bit-phase one of <gsdr/adjust_frequency.h>; numOutputs + 1 low-pass values are produced internally, so
+ *
+ *   input must hold numOutputs * decimation + numLowPassTaps elements
+ *
+ * (the reference's header says (numOutputs + 1) * decimation, which is what its kernel would read only if
+ * numLowPassTaps <= decimation).  Repeated calls need the usual overlap (ref: include/gsdr/fm.h:26) and the
+ * running firstSampleIndex.  Scratch for the low-pass values is taken from the stream-ordered allocator
+ * (cudaMallocAsync / cudaFreeAsync on cudaStream): no synchronisation, capturable in a CUDA graph.
+ */
+#ifndef GSDR_B200_INCLUDE_GSDR_FM_H_
+#define GSDR_B200_INCLUDE_GSDR_FM_H_
+
+#include <cuComplex.h>
+#include <cuda_runtime.h>
+#include <gsdr/gsdr_export.h>
+#include <gsdr/util.h>
+#include <stddef.h>
+#include <stdint.h>
+
+GSDR_C_LINKAGE GSDR_PUBLIC cudaError_t gsdrFmDemod(
+    float rfSampleRate,
+    float tuningFrequency,
+    float channelFrequency,
+    float frequencyDeviation,
+    uint32_t decimation,
+    size_t firstSampleIndex,
+    const float* lowPassTaps,
+    size_t numLowPassTaps,
+    const cuComplex* input,
+    float* output,
+    size_t numOutputs,
+    int32_t cudaDevice,
+    cudaStream_t cudaStream) GSDR_NO_EXCEPT;
+
+#endif /* GSDR_B200_INCLUDE_GSDR_FM_H_ */

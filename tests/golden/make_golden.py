@@ -67,6 +67,17 @@ def main() -> None:
         np.savez(out_dir / f"ref_adjust_literal_{ci}.npz", kind="adjust_literal", sample_rate=fs, frequency_shift=f,
                  first_sample_index=first, decimation=D, num_outputs=n_out, seed=seed, taps=taps, input=x,
                  output=dy.cpu().numpy())
+    for ci, n_out in enumerate((1, 257, 4099)):
+        seed = 9500 + ci
+        rng = np.random.default_rng(seed)
+        x = _rand(rng, n_out + 1, True)
+        dx = torch.from_numpy(x).to(dev)
+        dy = torch.zeros(n_out, dtype=torch.float32, device=dev)
+        rc = ref_cuda.lib().gsdrQuadFmDemod(dx.data_ptr(), dy.data_ptr(), 1.5, n_out, 0, 0)
+        assert rc == 0
+        torch.cuda.synchronize()
+        np.savez(out_dir / f"ref_quadfm_{ci}.npz", kind="quad_fm", gain=1.5, num_outputs=n_out, seed=seed, input=x,
+                 output=dy.cpu().numpy())
     print(f"wrote {len(list(out_dir.glob('ref_*.npz')))} golden files to {out_dir}")
 
 

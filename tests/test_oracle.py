@@ -223,6 +223,10 @@ def test_oracle_reproduces_reference_cuda_bits(path):
         tol = 1e-5 * float(np.abs(z["taps"]).sum()) * float(np.abs(z["input"]).max())
         # sincospif differs by <= 2 ulp between CUDA and libm, so this one is tolerance-, not bit-, pinned
         assert np.abs(y - z["output"]).max() <= tol
+    elif kind == "quad_fm":
+        y = oracle.quad_fm_demod(z["input"], float(z["gain"]), int(z["num_outputs"]))
+        # ref: src/quad_demod.cu:23-37 — atan2f differs by a few ulp between CUDA and libm
+        assert np.abs(y - z["output"]).max() <= float(z["gain"]) * 4e-7 * math.pi
     else:
         pytest.fail(f"unknown golden kind {kind}")
 
