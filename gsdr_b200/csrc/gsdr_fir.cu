@@ -646,7 +646,7 @@ GSDR_C_LINKAGE int gsdrB200NumKernelVariants(void) GSDR_NO_EXCEPT { return kNumV
 GSDR_C_LINKAGE int gsdrB200NumPolyphaseVariants(void) GSDR_NO_EXCEPT { return kNumVariants; }
 
 GSDR_C_LINKAGE int gsdrB200SetDebugFlags(int flags) GSDR_NO_EXCEPT {
-  gDebugFlags.store(flags & 3, std::memory_order_relaxed);
+  gDebugFlags.store(flags & 7, std::memory_order_relaxed);
   return 0;
 }
 

@@ -85,7 +85,7 @@ def main():
         extra = {}
         if args.split and v >= 0:
             from gsdr_b200._lib import lib as _l
-            for name, flag in (("ms_copy_only", 2), ("ms_fir_only", 1)):
+            for name, flag in (("ms_copy_only", 2), ("ms_fir_only", 1), ("ms_fir_nostore", 5)):
                 _l.gsdrB200SetDebugFlags(flag)
                 extra[name] = timeit(lambda: fn(D, taps, T, x, y, n_out, 0, stream), stream, reps=10)[0]
             _l.gsdrB200SetDebugFlags(0)
