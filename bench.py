@@ -48,6 +48,13 @@ WORKLOADS = {
                        desc="1023-tap decimate-by-32 complex FIR without the NCO, 256Mi samples per GPU"),
     "cfg5s1": dict(D=10, T=255, n_in=1 << 28, nco=True,
                    desc="fused NCO mix + 255-tap decimate-by-10 (BASELINE config 5 stage 1 shape), 256Mi samples per GPU"),
+    # the two below have their own step functions (see main)
+    "cfg4": dict(D=4, T=127, n_in=1 << 22, nco=False, channels=1024,
+                 desc="1024 independent channels x 4Mi samples, 127-tap decimate-by-4, sharded by channel (BASELINE "
+                      "config 4; channels are split over the ranks: strong scaling)"),
+    "cfg5": dict(D=10, T=255, n_in=1 << 28, nco=True, chain=dict(D3=5, T3=63),
+                 desc="FM receive chain: NCO mix -> 255-tap FIR decim 10 -> quad demod -> 63-tap audio FIR decim 5, "
+                      "256Mi samples per GPU of one capture, time-sharded with the 835-sample halo (BASELINE config 5)"),
 }
 PAPER_FP32_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12  # 74.45
 
@@ -216,7 +223,57 @@ def main() -> None:
     stream = torch.cuda.Stream(device=dev)
     fs, fshift = 2.4e6, 29520.0
 
-    if args.impl == "reference":
+    special = None
+    if args.impl == "ours" and args.workload == "cfg4":
+        # ---- BASELINE config 4: channels sharded across ranks, one batched launch per rank ----
+        chans_total = wl["channels"]
+        c0, cn = g.shard_plan_channels(chans_total, world, rank)
+        n_out_c = g.fir_num_outputs(n_in_gpu, T, D)
+        base = synth.tone_plus_noise(0, n_in_gpu * 8, seed=0x5EED0004, device=dev).view(8, n_in_gpu)
+        xb = torch.empty((cn, n_in_gpu), dtype=torch.complex64, device=dev)
+        for c in range(cn):
+            xb[c].copy_(base[(c0 + c) % 8])
+            xb[c, : 1024] *= 1.0 + 0.001 * (c0 + c)  # channels are not bit-identical copies
+        yb = torch.zeros((cn, n_out_c), dtype=torch.complex64, device=dev)
+        del x, y, base
+
+        def step():
+            g.gsdrFirFCBatched(D, dtaps, T, 0, xb, n_in_gpu, yb, n_out_c, n_out_c, cn, local, stream)
+
+        n_in_total = n_in_gpu * chans_total
+        n_out_total = n_out_c * chans_total
+        special = dict(units_in=cn * n_in_gpu, units_out=cn * n_out_c, scaling="strong",
+                       sharding=f"channels: rank {rank} owns {cn} of {chans_total}; one batched launch per rank")
+    elif args.impl == "ours" and args.workload == "cfg5":
+        # ---- BASELINE config 5: the composite stage is a FIR with window 885 and stride 50 for planning ----
+        D3, T3 = wl["chain"]["D3"], wl["chain"]["T3"]
+        window, stride = D * T3 + T, D * D3  # 885, 50
+        n3_total = (n_in_total - window) // stride + 1
+        sh3 = g.shard_plan_time(n3_total, stride, window, 0, world, rank)
+        n3 = sh3.numOutputs
+        n2 = g.fir_num_inputs(n3, T3, D3)
+        del x, y
+        x5 = synth.tone_plus_noise(sh3.firstInput, sh3.numInputs, seed=0x5EED0005, device=dev,
+                                   tone_cycles_per_sample=300e3 / 2.4e6)
+        h3 = torch.from_numpy(synth.lowpass_taps(T3, D3)).to(dev)
+        dm = torch.zeros(n2, dtype=torch.float32, device=dev)
+        au = torch.zeros(n3, dtype=torch.float32, device=dev)
+
+        def step():
+            g.gsdrFmDemod(2.4e6, 100.0e6, 100.3e6, 75e3, D, sh3.firstSampleIndex, dtaps, T, x5, dm, n2, local, stream)
+            g.gsdrFirFF(D3, h3, T3, dm, au, n3, local, stream)
+
+        n_out_total = n3_total
+        special = dict(units_in=sh3.numInputs, units_out=n2 + 1, scaling="weak",
+                       sharding=f"time blocks of the final audio outputs; halo {window - stride} input samples")
+        args.no_e2e = True
+    if special is not None:
+        args.no_e2e = True
+        args.gather = False
+
+    if special is not None:
+        pass
+    elif args.impl == "reference":
         from oracle import ref_cuda
 
         if not ref_cuda.available():
@@ -264,8 +321,10 @@ def main() -> None:
 
     # ---- roofline of the dominant (only) kernel: algorithmic bytes and flops per launch ----
     hbm_peak, hbm_src = _peaks()
-    bytes_alg = 8 * sh.numInputs + 8 * sh.numOutputs + 4 * T  # each input once, each output once, taps once
-    flops_alg = 4.0 * T * sh.numOutputs                       # FC: 4*T flops per complex output
+    units_in = special["units_in"] if special else sh.numInputs
+    units_out = special["units_out"] if special else sh.numOutputs
+    bytes_alg = 8 * units_in + 8 * units_out + 4 * T  # each input once, each output once, taps once
+    flops_alg = 4.0 * T * units_out                   # FC: 4*T flops per complex output (dominant kernel)
     kernel_s = (e0.elapsed_time(e1) / args.steps) * 1e-3      # this rank's average launch duration
     ffma_tf, ffma2_tf = _fp32_peak(local)
     fp32_peak = max([v for v in (ffma_tf, ffma2_tf) if v] or [PAPER_FP32_TFLOPS])
@@ -360,13 +419,15 @@ def main() -> None:
     info = g.describe_kernel(4 if wl["nco"] else 0, D, T, sh.numOutputs, local) if args.impl == "ours" else None
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "ms_per_step": ms_step, "higher_is_better": True, "scaling": special["scaling"] if special else "weak",
+        "vs_baseline": None, "dtype": "f32",
         "data": "synthetic", "impl": args.impl,
         "config": {
             "workload": wl["desc"], "decimation": D, "taps": T, "input_samples_per_gpu": n_in_gpu,
             "input_samples_total": n_in_total, "outputs_total": n_out_total,
-            "sharding": "time blocks of one capture, (taps-decimation)-sample overlap resident per rank, no collective"
-            if world > 1 else "single GPU",
+            "sharding": special["sharding"] if special else (
+                "time blocks of one capture, (taps-decimation)-sample overlap resident per rank, no collective"
+                if world > 1 else "single GPU"),
             "l2": "input (537 MB/GPU) larger than the 126 MB L2; no explicit flush",
             "timing": "CUDA events on the launching stream around K back-to-back launches, max over ranks",
             "kernel": (f"{'TMA-fed' if info.variant >= g.num_polyphase_variants() else 'cp.async-staged'} persistent "
@@ -375,7 +436,8 @@ def main() -> None:
                        f"{info.sharedBytesPerBlock} B smem, {info.numBlocks} tiles") if info else
             "reference k_FirDecimate<float2,float2,float> (32-thread blocks, one thread per output)",
         },
-        "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": args.steps, "clocks": sampler.summary(),
+        "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": args.steps * (3 if args.workload == "cfg5" and args.impl == "ours" else 1),
+        "clocks": sampler.summary(),
     }
     if gather_ms is not None:
         line["gather_ms"] = gather_ms

@@ -246,21 +246,30 @@ __device__ __forceinline__ void tmaMixWindow(unsigned char* buf, unsigned long l
       ncoA[(m & 7u) * mhCount + (m >> 3)] = ncoExactPhasor(P.ncoFirst + in0 + (unsigned long long)m * D, P.ncoStep);
     }
     __syncthreads();
-    const unsigned total = pairsPerRow * rows;
-    unsigned g = threadIdx.x / mhCount;  // g = pp * 8 + ml
+    // pass 2: work item = (chunk of up to 4 branch pairs, plane, row group); the row anchor is loaded once per item
+    const unsigned pairsPerChunk = (pairsPerRow % 4u == 0u) ? 4u : 1u;  // finer items balance better for odd counts
+    const unsigned chunks = pairsPerRow / pairsPerChunk;
+    const unsigned total = chunks * rows;
+    unsigned g = threadIdx.x / mhCount;  // g = chunk * 8 + ml
     unsigned mh = threadIdx.x - g * mhCount;
     const unsigned dg = NT / mhCount, dmh = NT - dg * mhCount;
     for (unsigned e = threadIdx.x; e < total; e += NT) {
-      const unsigned pp = g >> 3, ml = g & 7u;
+      const unsigned ck = g >> 3, ml = g & 7u;
       const float2 an = ncoA[ml * mhCount + mh];
-      const float4 rr = *reinterpret_cast<const float4*>(ncoR + 2u * pp);
-      float4* q = reinterpret_cast<float4*>(buf + ml * planeBytes + tmaPairOffset<DT>(mh, pp, planeBytes, P));
-      const float4 v = *q;
-      const float2 w0 = cmulf(an, make_float2(rr.x, rr.y));
-      const float2 w1 = cmulf(an, make_float2(rr.z, rr.w));
-      const float2 a = cmulf(make_float2(v.x, v.y), w0);
-      const float2 c = cmulf(make_float2(v.z, v.w), w1);
-      *q = make_float4(a.x, a.y, c.x, c.y);
+      unsigned char* rowBase = buf + ml * planeBytes;
+      const unsigned pp0 = ck * pairsPerChunk;
+#pragma unroll 4
+      for (unsigned k = 0; k < pairsPerChunk; k++) {
+        const unsigned pp = pp0 + k;
+        const float4 rr = *reinterpret_cast<const float4*>(ncoR + 2u * pp);
+        float4* q = reinterpret_cast<float4*>(rowBase + tmaPairOffset<DT>(mh, pp, planeBytes, P));
+        const float4 v = *q;
+        const float2 w0 = cmulf(an, make_float2(rr.x, rr.y));
+        const float2 w1 = cmulf(an, make_float2(rr.z, rr.w));
+        const float2 a = cmulf(make_float2(v.x, v.y), w0);
+        const float2 c = cmulf(make_float2(v.z, v.w), w1);
+        *q = make_float4(a.x, a.y, c.x, c.y);
+      }
       g += dg;
       mh += dmh;
       if (mh >= mhCount) {

@@ -348,13 +348,15 @@ static int chooseTmaVariant(const FirCall& c, int maxSmem, TmaGeom* geom) noexce
   static const int orderEvenPairs[] = {1, 8, 5, 0};   // D = 8, 16: the branch pairs split evenly over 2 groups
   static const int orderOddPairs[] = {8, 1, 5, 0};    // D = 2, 4, 6, 10, 14: one group keeps all pairs
   static const int orderWide[] = {4, 10, 11, 1};
-  static const int orderNarrowNco[] = {10, 5, 1, 8};
+  static const int orderNarrowNcoEven[] = {6, 9, 5, 1};  // 6 = (64 x 2, single buffer), 9 = (64 x 1, single buffer)
+  static const int orderNarrowNcoOdd[] = {9, 6, 5, 1};
   static const int orderWideNco[] = {10, 11, 4, 1};
   const bool wide = c.decimation > 16;
   const bool nco = c.nco != kNcoNone;
   const bool evenPairs = ((c.decimation / 2) % 2 == 0) && c.decimation >= 8;
   const int* order = wide ? (nco ? orderWideNco : orderWide)
-                          : (nco ? orderNarrowNco : (evenPairs ? orderEvenPairs : orderOddPairs));
+                          : (nco ? (evenPairs ? orderNarrowNcoEven : orderNarrowNcoOdd)
+                                 : (evenPairs ? orderEvenPairs : orderOddPairs));
   const int orderLen = 4;
   for (int k = 0; k < orderLen; k++) {
     const int id = order[k];

@@ -17,8 +17,9 @@
  *
  * (the reference's header says (numOutputs + 1) * decimation, which is what its kernel would read only if
  * numLowPassTaps <= decimation).  Repeated calls need the usual overlap (ref: include/gsdr/fm.h:26) and the
- * running firstSampleIndex.  Scratch for the low-pass values is taken from the stream-ordered allocator
- * (cudaMallocAsync / cudaFreeAsync on cudaStream): no synchronisation, capturable in a CUDA graph.
+ * running firstSampleIndex.  Scratch for the low-pass values is taken from a library-private stream-ordered memory
+ * pool (cudaMallocFromPoolAsync / cudaFreeAsync on cudaStream): no synchronisation, capturable in a CUDA graph,
+ * and the device's default pool is not touched.
  */
 #ifndef GSDR_B200_INCLUDE_GSDR_FM_H_
 #define GSDR_B200_INCLUDE_GSDR_FM_H_

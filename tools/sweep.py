@@ -42,6 +42,7 @@ def main():
     ap.add_argument("--kind", default="fc")
     ap.add_argument("--ref", action="store_true")
     ap.add_argument("--peaks", action="store_true")
+    ap.add_argument("--nco", action="store_true", help="time gsdrAdjustFrequencyFirFC instead of gsdrFirFC")
     ap.add_argument("--split", action="store_true", help="also time copy-only and FIR-only halves of each variant")
     args = ap.parse_args()
     dev = torch.device("cuda:0")
@@ -54,6 +55,9 @@ def main():
     y = torch.zeros(n_out, dtype=torch.float32 if real else torch.complex64, device=dev)
     stream = torch.cuda.Stream()
     fn = g.gsdrFirFF if real else g.gsdrFirFC
+    if args.nco:
+        def fn(D_, taps_, T_, x_, y_, n_, dev_, stream_):  # noqa: E306
+            g.gsdrAdjustFrequencyFirFC(2.4e6, 29520.0, 12345, D_, taps_, T_, x_, y_, n_, dev_, stream_)
     esz = 4 if real else 8
     bytes_alg = esz * n_in + esz * n_out + 4 * T
     flops = (2.0 if real else 4.0) * T * n_out
@@ -73,12 +77,16 @@ def main():
     ref = None
     for v in list(range(g.num_kernel_variants())) + [-2]:
         g.set_kernel_variant(v)
-        info = g.describe_kernel(1 if real else 0, D, T, n_out)
+        info = g.describe_kernel(1 if real else (4 if args.nco else 0), D, T, n_out)
         if v >= 0 and info.variant != v:
             print(json.dumps({"variant": v, "skipped": "does not fit"}), flush=True)
             continue
         y.zero_()
-        med, best = timeit(lambda: fn(D, taps, T, x, y, n_out, 0, stream), stream, reps=5 if v == -2 else 20)
+        try:
+            med, best = timeit(lambda: fn(D, taps, T, x, y, n_out, 0, stream), stream, reps=5 if v == -2 else 20)
+        except g.CudaError as e:
+            print(json.dumps({"variant": v, "skipped": str(e)}), flush=True)
+            continue
         if ref is None:
             ref = y.clone()
         diff = float((y - ref).abs().max())
