@@ -23,6 +23,7 @@ NVCC_FLAGS = [
     "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC,-fvisibility=hidden",
     "-Xptxas", "-v",
+    "-split-compile", "0",  # ptxas over all host cores: ~150 template instantiations of the big kernels
 ]
 
 

@@ -194,12 +194,13 @@ __device__ __forceinline__ void firPairBlock(
 // 8-byte cp.async with zero fill beyond the caller-guaranteed extent.
 template <int NT, int DT>
 __device__ __forceinline__ void tmaStageSlow(unsigned char* buf, const float2* src, unsigned long long in0,
-                                             unsigned rows, unsigned planeBytes, const TmaParams& P) {
+                                             unsigned rows, unsigned planeBytes, const TmaParams& P,
+                                             unsigned lt = threadIdx.x) {
   const unsigned D = DT ? (unsigned)DT : P.D;
   const unsigned total = rows * D;
-  unsigned p = threadIdx.x % D, m = threadIdx.x / D;
+  unsigned p = lt % D, m = lt / D;
   const unsigned dp = NT % D, dm = NT / D;
-  for (unsigned s = threadIdx.x; s < total; s += NT) {
+  for (unsigned s = lt; s < total; s += NT) {
     const unsigned long long g = in0 + s;
     const bool valid = g < P.nIn;
     cpAsync8z(buf + tmaSampleOffset<DT>(m, p, planeBytes, P), src + (valid ? g : 0ull), valid);
@@ -233,27 +234,37 @@ __device__ __forceinline__ float2 cmulf(float2 a, float2 b) {
 // tiles start on multiples of D), so time shards reproduce the unsharded bits.  Work items are (branch pair,
 // plane, row group) with consecutive lanes on consecutive row groups, like the FIR reader (conflict free).
 // Literal mode (parity with the reference only): the reference's arithmetic per sample.
-template <int MODE, int NT, int DT>
+// Barrier among the NT threads that run a mix pass: the whole CTA (id 0) or the mixer warps only (named barrier).
+template <int NT, int BARRIER_ID>
+__device__ __forceinline__ void mixBarrier() {
+  if (BARRIER_ID == 0) {
+    __syncthreads();
+  } else {
+    asm volatile("bar.sync %0, %1;" ::"n"(BARRIER_ID), "n"(NT) : "memory");
+  }
+}
+
+template <int MODE, int NT, int DT, int BARRIER_ID = 0>
 __device__ __forceinline__ void tmaMixWindow(unsigned char* buf, unsigned long long in0, unsigned rows,
                                              unsigned planeBytes, float2* ncoA, const float2* ncoR,
-                                             const TmaParams& P) {
+                                             const TmaParams& P, unsigned lt = threadIdx.x) {
   const unsigned D = DT ? (unsigned)DT : P.D;
   const unsigned pairsPerRow = D >> 1;
   if (MODE == kPolyNcoExact) {
     const unsigned mhCount = rows >> 3;  // rows is a multiple of 8
     // pass 1: row anchors, stored [ml][mh] so that pass 2 reads them with consecutive lanes
-    for (unsigned m = threadIdx.x; m < rows; m += NT) {
+    for (unsigned m = lt; m < rows; m += NT) {
       ncoA[(m & 7u) * mhCount + (m >> 3)] = ncoExactPhasor(P.ncoFirst + in0 + (unsigned long long)m * D, P.ncoStep);
     }
-    __syncthreads();
+    mixBarrier<NT, BARRIER_ID>();
     // pass 2: work item = (chunk of up to 4 branch pairs, plane, row group); the row anchor is loaded once per item
     const unsigned pairsPerChunk = (pairsPerRow % 4u == 0u) ? 4u : 1u;  // finer items balance better for odd counts
     const unsigned chunks = pairsPerRow / pairsPerChunk;
     const unsigned total = chunks * rows;
-    unsigned g = threadIdx.x / mhCount;  // g = chunk * 8 + ml
-    unsigned mh = threadIdx.x - g * mhCount;
+    unsigned g = lt / mhCount;  // g = chunk * 8 + ml
+    unsigned mh = lt - g * mhCount;
     const unsigned dg = NT / mhCount, dmh = NT - dg * mhCount;
-    for (unsigned e = threadIdx.x; e < total; e += NT) {
+    for (unsigned e = lt; e < total; e += NT) {
       const unsigned ck = g >> 3, ml = g & 7u;
       const float2 an = ncoA[ml * mhCount + mh];
       unsigned char* rowBase = buf + ml * planeBytes;
@@ -279,7 +290,7 @@ __device__ __forceinline__ void tmaMixWindow(unsigned char* buf, unsigned long l
     }
   } else {
     const unsigned total = rows * pairsPerRow;
-    for (unsigned e = threadIdx.x; e < total; e += NT) {
+    for (unsigned e = lt; e < total; e += NT) {
       const unsigned m = e / pairsPerRow;
       const unsigned pp = e - m * pairsPerRow;
       float4* q = reinterpret_cast<float4*>(buf + tmaSampleOffset<DT>(m, 2 * pp, planeBytes, P));
@@ -533,6 +544,163 @@ __global__ void __launch_bounds__(TG* PSPLIT, MINB)
     tile = nextTile;
   }
   asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Warp-specialised variant for the fused NCO (exact phase law): the CTA's first TG*PSPLIT threads only filter,
+// MIXW extra warps only copy and mix.  Tile k+1 is fetched (TMA) and mixed in place by the mixer warps while the
+// FIR warps filter tile k; everything is handed over with mbarriers, so the mix pass (latency bound: sincospi,
+// table look-ups, read-modify-write of shared memory) fills the issue slots the FIR leaves, instead of
+// alternating with it.
+//   fullRaw[b]  TMA bytes of buffer b have landed            (tx count, armed by mixer thread 0)
+//   fullMix[b]  buffer b is mixed                             (every mixer thread arrives)
+//   empty[b]    the FIR warps are done reading buffer b       (every FIR thread arrives)
+// One tap set for all channels only (hStride == 0); the host falls back to firTmaKernel otherwise.
+// ---------------------------------------------------------------------------------------------------------
+template <int TG, int PSPLIT, int DT, int MIXW, int MINB>
+__global__ void __launch_bounds__(TG* PSPLIT + 32 * MIXW, MINB)
+    firTmaNcoSpecKernel(const __grid_constant__ CUtensorMap map, const TmaParams P) {
+  constexpr unsigned NTF = TG * PSPLIT;  // filter threads
+  constexpr unsigned NTM = 32 * MIXW;    // mixer threads
+  constexpr unsigned BOUT = kTmaR * TG;
+  extern __shared__ __align__(16) unsigned char smemRaw[];
+  __shared__ __align__(8) unsigned long long fullRaw[2], fullMix[2], emptyBar[2];
+  const unsigned D = DT ? (unsigned)DT : P.D;
+  const unsigned rowBytes = 8u * D;
+  const unsigned segBytes = DT ? tmaSegBytes(DT ? DT : 2) : P.segBytes;
+  const unsigned numSegs = rowBytes / segBytes;
+  const unsigned planeBytes = DT ? tmaPlaneRows(TG, kTmaJpadCap, DT ? DT : 2) * segBytes : P.planeBytes;
+  const unsigned bufBytes = numSegs * 8u * planeBytes;
+  unsigned char* bufBase = smemRaw + ((1024u - (smemU32(smemRaw) & 1023u)) & 1023u);
+  float4* scratch = reinterpret_cast<float4*>(bufBase + 2u * bufBytes);
+  float* hs = reinterpret_cast<float*>(scratch + 2u * (PSPLIT - 1) * (kTmaR / 2) * TG);
+  float2* ncoA = reinterpret_cast<float2*>(hs + (size_t)D * P.Jpad + 32u);
+  float2* ncoR = ncoA + (BOUT + P.Jpad);
+
+  const unsigned tid = threadIdx.x;
+  const unsigned rowsStaged = BOUT + P.Jpad;
+  if (tid == 0) {
+    for (int b = 0; b < 2; b++) {
+      mbarInit(&fullRaw[b], 1);
+      mbarInit(&fullMix[b], NTM);
+      mbarInit(&emptyBar[b], NTF);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  for (unsigned p = tid; p < D; p += NTF + NTM) ncoR[p] = ncoExactPhasor((unsigned long long)p, P.ncoStep);
+  {
+    const unsigned nh = D * P.Jpad;
+    for (unsigned i = tid; i < nh + 32u; i += NTF + NTM) {
+      const unsigned pp = i / (2u * P.Jpad);
+      const unsigned rem = i - pp * 2u * P.Jpad;
+      const unsigned ti = (rem >> 1) * D + 2u * pp + (rem & 1u);
+      hs[i] = (i < nh && ti < P.T) ? __ldg(P.h + ti) : 0.0f;
+    }
+  }
+  __syncthreads();
+
+  unsigned chan = blockIdx.x / P.tilesPerChannel;
+  unsigned tile = blockIdx.x - chan * P.tilesPerChannel;
+  auto advance = [&](unsigned& c, unsigned& tl) {
+    c += P.strideChan;
+    tl += P.strideTile;
+    if (tl >= P.tilesPerChannel) {
+      tl -= P.tilesPerChannel;
+      c += 1;
+    }
+  };
+  auto tileIsFast = [&](unsigned tl) -> bool { return tl * BOUT + rowsStaged <= P.tmaRows; };
+
+  if (tid >= NTF) {
+    // ===================== mixer warps: copy + mix, up to two tiles ahead of the filter warps =====================
+    const unsigned lt = tid - NTF;
+    for (unsigned k = 0; chan < P.numChannels; k++, advance(chan, tile)) {
+      const unsigned b = k & 1u;
+      unsigned char* buf = bufBase + b * bufBytes;
+      if (k >= 2) mbarWait(&emptyBar[b], ((k >> 1) - 1u) & 1u);  // the filter warps have left tile k-2
+      const bool fast = tileIsFast(tile);
+      if (fast) {
+        if (lt == 0) {
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          mbarExpectTx(&fullRaw[b], bufBytes);
+          for (unsigned sg = 0; sg < numSegs; sg++) {
+            tmaLoad4(buf + sg * 8u * planeBytes, &map, &fullRaw[b], (int)(sg * (segBytes / 4u)),
+                     (int)(tile * (BOUT / 8)), 0, (int)chan);
+          }
+        }
+        mbarWait(&fullRaw[b], (k >> 1) & 1u);
+      } else {
+        if (lt == 0) mbarArrive(&fullRaw[b]);  // keep the phase of the unused barrier in step with k
+        tmaStageSlow<NTM, DT>(buf, P.x + (size_t)chan * P.xStride, (unsigned long long)tile * BOUT * D, rowsStaged,
+                              planeBytes, P, lt);
+        asm volatile("cp.async.commit_group;\n" ::: "memory");
+        asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+        mixBarrier<NTM, 1>();
+      }
+      tmaMixWindow<kPolyNcoExact, NTM, DT, 1>(buf, (unsigned long long)tile * BOUT * D, rowsStaged, planeBytes, ncoA,
+                                              ncoR, P, lt);
+      mbarArrive(&fullMix[b]);   // release: the mixed window is visible to whoever acquires the barrier
+      mixBarrier<NTM, 1>();      // ncoA may be overwritten by the next tile's anchors
+    }
+    return;
+  }
+
+  // ============================== filter warps ==============================
+  const unsigned grp = tid / TG;
+  const unsigned t = tid - grp * TG;
+  const unsigned numPairs = D >> 1;
+  const unsigned ppBegin = (grp * numPairs) / PSPLIT;
+  const unsigned ppEnd = ((grp + 1) * numPairs) / PSPLIT;
+  for (unsigned k = 0; chan < P.numChannels; k++, advance(chan, tile)) {
+    const unsigned b = k & 1u;
+    const unsigned char* buf = bufBase + b * bufBytes;
+    const unsigned long long o0 = (unsigned long long)tile * BOUT;
+    mbarWait(&fullMix[b], (k >> 1) & 1u);
+    float2 acc[kTmaR];
+#pragma unroll
+    for (int r = 0; r < kTmaR; r++) acc[r] = make_float2(0.0f, 0.0f);
+    if (ppBegin < ppEnd) firComputePairs<DT>(acc, buf, hs, t, ppBegin, ppEnd, P.Jpad, planeBytes, P);
+    mbarArrive(&emptyBar[b]);  // this thread has no more reads of the window
+    if (PSPLIT > 1) {
+      float4* red = scratch + (size_t)(k & 1u) * (PSPLIT - 1) * (kTmaR / 2) * TG;
+      if (grp > 0) {
+#pragma unroll
+        for (int q = 0; q < kTmaR / 2; q++) {
+          red[((grp - 1) * (kTmaR / 2) + q) * TG + t] =
+              make_float4(acc[2 * q].x, acc[2 * q].y, acc[2 * q + 1].x, acc[2 * q + 1].y);
+        }
+      }
+      asm volatile("bar.sync 2, %0;" ::"n"(NTF) : "memory");
+      if (grp == 0) {
+#pragma unroll
+        for (int g = 1; g < PSPLIT; g++) {
+#pragma unroll
+          for (int q = 0; q < kTmaR / 2; q++) {
+            const float4 v = red[((g - 1) * (kTmaR / 2) + q) * TG + t];
+            acc[2 * q].x += v.x;
+            acc[2 * q].y += v.y;
+            acc[2 * q + 1].x += v.z;
+            acc[2 * q + 1].y += v.w;
+          }
+        }
+      }
+    }
+    if (grp == 0) {
+      const unsigned long long ob = o0 + (unsigned long long)t * kTmaR;
+      float2* y = P.y + (size_t)chan * P.yStride;
+      if (P.y16 && ob + kTmaR <= P.nOut) {
+#pragma unroll
+        for (int r = 0; r < kTmaR; r += 2) {
+          *reinterpret_cast<float4*>(y + ob + r) = make_float4(acc[r].x, acc[r].y, acc[r + 1].x, acc[r + 1].y);
+        }
+      } else {
+#pragma unroll
+        for (int r = 0; r < kTmaR; r++) {
+          if (ob + r < P.nOut) y[ob + r] = acc[r];
+        }
+      }
+    }
+  }
 }
 
 }  // namespace gsdr_b200

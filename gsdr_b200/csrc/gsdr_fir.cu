@@ -208,6 +208,26 @@ static constexpr TmaVariant kTmaVariants[] = {
 };
 static constexpr int kNumTmaVariants = (int)(sizeof(kTmaVariants) / sizeof(kTmaVariants[0]));
 
+// Warp-specialised fused-NCO kernel: X(id, TG, PSPLIT, MIXW, MINB); ids continue after the TMA variants
+#define GSDR_SPEC_VARIANTS(X) \
+  X(0, 32, 2, 2, 4)           \
+  X(1, 32, 4, 4, 1)           \
+  X(2, 64, 2, 4, 2)           \
+  X(3, 32, 1, 1, 4)           \
+  X(4, 32, 2, 1, 4)           \
+  X(5, 32, 4, 2, 2)
+
+struct SpecVariant {
+  int tg, psplit, mixw, minBlocks;
+  int threads() const { return tg * psplit + 32 * mixw; }
+};
+static constexpr SpecVariant kSpecVariants[] = {
+#define X(id, tg, ps, mw, mb) {tg, ps, mw, mb},
+    GSDR_SPEC_VARIANTS(X)
+#undef X
+};
+static constexpr int kNumSpecVariants = (int)(sizeof(kSpecVariants) / sizeof(kSpecVariants[0]));
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -298,6 +318,60 @@ static cudaError_t launchTmaT(const CUtensorMap& map, TmaParams& P, size_t smem,
   return cudaLaunchKernel((const void*)kernel, dim3(grid), dim3(TG * PSPLIT), args, smem, stream);
 }
 
+template <int TG, int PSPLIT, int DT, int MIXW, int MINB>
+static cudaError_t launchSpecT(const CUtensorMap& map, TmaParams& P, size_t smem, int dev, int smCount,
+                               cudaStream_t stream) noexcept {
+  static std::atomic<size_t> configured[64];
+  auto kernel = firTmaNcoSpecKernel<TG, PSPLIT, DT, MIXW, MINB>;
+  constexpr int kThreads = TG * PSPLIT + 32 * MIXW;
+  if (smem > configured[dev & 63].load(std::memory_order_acquire)) {
+    cudaError_t st = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (st != cudaSuccess) return report(st, "cudaFuncSetAttribute(MaxDynamicSharedMemorySize)");
+    configured[dev & 63].store(smem, std::memory_order_release);
+  }
+  int perSm = 0;
+  cudaError_t st = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, kernel, kThreads, smem);
+  if (st != cudaSuccess) return report(st, "cudaOccupancyMaxActiveBlocksPerMultiprocessor");
+  if (perSm < 1) return cudaErrorInvalidConfiguration;
+  {
+    const int warpsPerCta = kThreads / 32;
+    int balanced = perSm;
+    while (balanced > 1 && (balanced * warpsPerCta) % 4 != 0) balanced--;
+    if ((balanced * warpsPerCta) % 4 == 0) perSm = balanced;
+  }
+  const unsigned long long resident = (unsigned long long)perSm * (unsigned)smCount;
+  const unsigned grid = (unsigned)(P.totalTiles < resident ? P.totalTiles : resident);
+  P.strideChan = grid / P.tilesPerChannel;
+  P.strideTile = grid % P.tilesPerChannel;
+  void* args[] = {(void*)&map, (void*)&P};
+  return cudaLaunchKernel((const void*)kernel, dim3(grid), dim3(kThreads), args, smem, stream);
+}
+
+template <int DT>
+static cudaError_t launchSpecD(int variant, const CUtensorMap& map, TmaParams& P, size_t smem, int dev, int smCount,
+                               cudaStream_t stream) noexcept {
+  switch (variant) {
+#define X(id, tg, ps, mw, mb) \
+  case id: return launchSpecT<tg, ps, DT, mw, mb>(map, P, smem, dev, smCount, stream);
+    GSDR_SPEC_VARIANTS(X)
+#undef X
+    default: return cudaErrorInvalidValue;
+  }
+}
+
+static cudaError_t launchSpec(int variant, bool staticD, const CUtensorMap& map, TmaParams& P, size_t smem, int dev,
+                              int smCount, cudaStream_t stream) noexcept {
+  if (staticD) {
+    switch (P.D) {
+      case 8: return launchSpecD<8>(variant, map, P, smem, dev, smCount, stream);
+      case 10: return launchSpecD<10>(variant, map, P, smem, dev, smCount, stream);
+      case 32: return launchSpecD<32>(variant, map, P, smem, dev, smCount, stream);
+      default: break;
+    }
+  }
+  return launchSpecD<0>(variant, map, P, smem, dev, smCount, stream);
+}
+
 template <int MODE, int DT>
 static cudaError_t launchTmaModeD(int variant, const CUtensorMap& map, TmaParams& P, size_t smem, int dev,
                                   int smCount, cudaStream_t stream) noexcept {
@@ -325,6 +399,34 @@ static cudaError_t launchTmaMode(int variant, bool staticD, const CUtensorMap& m
   return launchTmaModeD<MODE, 0>(variant, map, P, smem, dev, smCount, stream);
 }
 
+// TMA-kernel variant ids: [0, kNumTmaVariants) = firTmaKernel, then the warp-specialised fused-NCO kernel.
+static bool tmaVariantShape(int id, TmaVariant* v, int* mixw) noexcept {
+  if (id >= 0 && id < kNumTmaVariants) {
+    *v = kTmaVariants[id];
+    *mixw = 0;
+    return true;
+  }
+  const int sid = id - kNumTmaVariants;
+  if (sid >= 0 && sid < kNumSpecVariants) {
+    *v = TmaVariant{kSpecVariants[sid].tg, kSpecVariants[sid].psplit, 2, kSpecVariants[sid].minBlocks};
+    *mixw = kSpecVariants[sid].mixw;
+    return true;
+  }
+  return false;
+}
+
+static bool tmaVariantFits(int id, const FirCall& c, int maxSmem, TmaGeom* geom) noexcept {
+  TmaVariant v;
+  int mixw = 0;
+  if (!tmaVariantShape(id, &v, &mixw)) return false;
+  if (mixw > 0) {
+    // the specialised kernel: exact NCO, one tap set for every channel
+    if (c.nco != kNcoExact) return false;
+    if (c.numChannels > 1 && c.tapStride != 0) return false;
+  }
+  return tmaGeometry(v, c.decimation, c.tapCount, geom) && geom->smemBytes <= (size_t)maxSmem;
+}
+
 // Returns the TMA variant to use for this call, or -1 when the call does not qualify.
 static int chooseTmaVariant(const FirCall& c, int maxSmem, TmaGeom* geom) noexcept {
   if (c.type != kFirFC) return -1;
@@ -335,10 +437,15 @@ static int chooseTmaVariant(const FirCall& c, int maxSmem, TmaGeom* geom) noexce
   const int forced = gForcedVariant.load(std::memory_order_relaxed);
   if (forced >= kNumVariants) {
     const int id = forced - kNumVariants;
-    return (id < kNumTmaVariants && tmaGeometry(kTmaVariants[id], c.decimation, c.tapCount, geom) &&
-            geom->smemBytes <= (size_t)maxSmem) ? id : -1;
+    return tmaVariantFits(id, c, maxSmem, geom) ? id : -1;
   }
   if (forced != -1) return -1;
+  if (c.nco == kNcoExact) {
+    // fused NCO: copy + mix on dedicated warps, overlapped with the FIR of the previous tile
+    // (tools/sweep.py --nco: 64 x 2 filter threads + 4 mixer warps for narrow rows, 32 x 4 + 4 for wide rows)
+    const int sid = kNumTmaVariants + (c.decimation > 16 ? 1 : 2);
+    if (tmaVariantFits(sid, c, maxSmem, geom)) return sid;
+  }
   // hand-tuned preference (tools/sweep.py): narrow rows -> 32 outputs-threads x 2 branch groups, double buffered;
   // wide rows (many branch pairs, big windows) -> 4 or 8 branch groups on a single buffer, 2 CTAs per SM
   // With the fused NCO every CTA alternates a mix pass (latency bound) and the FIR: more, single-buffered CTAs per
@@ -361,7 +468,7 @@ static int chooseTmaVariant(const FirCall& c, int maxSmem, TmaGeom* geom) noexce
   for (int k = 0; k < orderLen; k++) {
     const int id = order[k];
     TmaGeom g;
-    if (tmaGeometry(kTmaVariants[id], c.decimation, c.tapCount, &g) && g.smemBytes <= (size_t)maxSmem) {
+    if (tmaVariantFits(id, c, maxSmem, &g)) {
       *geom = g;
       return id;
     }
@@ -371,7 +478,9 @@ static int chooseTmaVariant(const FirCall& c, int maxSmem, TmaGeom* geom) noexce
 
 static cudaError_t launchTma(const FirCall& c, int variant, const TmaGeom& geom, int dev, int smCount,
                              cudaStream_t stream) noexcept {
-  const TmaVariant& v = kTmaVariants[variant];
+  TmaVariant v;
+  int mixw = 0;
+  if (!tmaVariantShape(variant, &v, &mixw)) return cudaErrorInvalidValue;
   const size_t bout = (size_t)kTmaR * v.tg;
   const unsigned long long tiles = (c.numOutputs + bout - 1) / bout;
   const unsigned long long total = tiles * c.numChannels;
@@ -429,6 +538,9 @@ static cudaError_t launchTma(const FirCall& c, int variant, const TmaGeom& geom,
       return cudaErrorInvalidValue;
     }
     if (tmaRows < 8) P.tmaRows = 0;
+  }
+  if (mixw > 0) {
+    return launchSpec(variant - kNumTmaVariants, geom.staticD, map, P, geom.smemBytes, dev, smCount, stream);
   }
   switch (c.nco) {
     case kNcoNone:
@@ -639,12 +751,14 @@ GSDR_C_LINKAGE uint64_t gsdrNcoPhaseStep(float frequencyShift, float sampleRate)
 // ---- tuning / introspection hooks of <gsdr/b200.h> -------------------------------------------------------
 
 GSDR_C_LINKAGE int gsdrB200SetKernelVariant(int variant) GSDR_NO_EXCEPT {
-  if (variant < -2 || variant >= kNumVariants + kNumTmaVariants) return -1;
+  if (variant < -2 || variant >= kNumVariants + kNumTmaVariants + kNumSpecVariants) return -1;
   gForcedVariant.store(variant, std::memory_order_relaxed);
   return 0;
 }
 
-GSDR_C_LINKAGE int gsdrB200NumKernelVariants(void) GSDR_NO_EXCEPT { return kNumVariants + kNumTmaVariants; }
+GSDR_C_LINKAGE int gsdrB200NumKernelVariants(void) GSDR_NO_EXCEPT {
+  return kNumVariants + kNumTmaVariants + kNumSpecVariants;
+}
 GSDR_C_LINKAGE int gsdrB200NumPolyphaseVariants(void) GSDR_NO_EXCEPT { return kNumVariants; }
 
 GSDR_C_LINKAGE int gsdrB200SetDebugFlags(int flags) GSDR_NO_EXCEPT {
@@ -674,12 +788,15 @@ GSDR_C_LINKAGE int gsdrB200DescribeKernel(int firType, size_t decimation, size_t
     TmaGeom tg{};
     const int tv = chooseTmaVariant(probe, di->maxSmemOptin, &tg);
     if (tv >= 0) {
-      const size_t bout = (size_t)kTmaR * kTmaVariants[tv].tg;
+      TmaVariant vs;
+      int mixw = 0;
+      tmaVariantShape(tv, &vs, &mixw);
+      const size_t bout = (size_t)kTmaR * vs.tg;
       info->variant = kNumVariants + tv;
       info->outputsPerThread = kTmaR;
-      info->threadsPerBlock = kTmaVariants[tv].threads();
-      info->phaseGroups = kTmaVariants[tv].psplit;
-      info->windowBuffers = kTmaVariants[tv].nbuf;
+      info->threadsPerBlock = vs.threads() + 32 * mixw;
+      info->phaseGroups = vs.psplit;
+      info->windowBuffers = vs.nbuf;
       info->outputsPerBlock = bout;
       info->sharedBytesPerBlock = tg.smemBytes;
       info->numBlocks = (numOutputs + bout - 1) / bout;
