@@ -205,6 +205,8 @@ def main() -> None:
     from gsdr_b200 import dist as gd
 
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (there is no CPU fallback)"
+    # stdout carries exactly one JSON line: NCCL's version / debug lines go to stderr
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     if args.impl == "reference":
         world = 1
     else:
