@@ -56,6 +56,12 @@ struct TmaParams {
   float ncoFs, ncoF;
 };
 
+// firTmaRealKernel: x, y and the strides count floats, D is twice the caller's decimation
+struct RealParams : TmaParams {
+  unsigned long long nOutReal;  // the caller's output count (nOut = ceil(nOutReal / 2) output pairs)
+  unsigned rawFloats;           // floats of input one tile reads, a multiple of 4
+};
+
 constexpr int kTmaR = 8;
 constexpr unsigned kTmaJpadCap = 64;  // compile-time-geometry kernels hold up to 64 taps per branch (T <= 64*D)
 
@@ -358,6 +364,39 @@ __device__ __forceinline__ void firComputePairs(float2 (&acc)[kTmaR], const unsi
     firPairBlock<kBlkTail, true>(acc, q, hBP, hBQ, hAP, hAQ, a0, a1, planeBytes, tapNext + 16);
     a0 = a1;
     hp += 2u * Jpad;
+  }
+}
+
+// Same, for at most 8 taps per branch (Jpad == 8, one tap block): each pair is a prologue block followed at once by
+// the tail block, which reads block 0 (A) as its old set and refills it with the next pair's block 0.
+template <int DT>
+__device__ __forceinline__ void firComputePairsShort(float2 (&acc)[kTmaR], const unsigned char* buf, const float* hs,
+                                                     unsigned t, unsigned ppBegin, unsigned ppStop,
+                                                     unsigned planeBytes, const TmaParams& P) {
+  auto blockAddr = [&](unsigned pp, unsigned c) -> const unsigned char* {
+    return buf + tmaPairOffset<DT>(t + c, pp, planeBytes, P);
+  };
+  const float* hp = hs + (size_t)ppBegin * 16u;
+  float hAP[8], hAQ[8], hBP[8], hBQ[8];
+  float4 q[8];
+#pragma unroll
+  for (int k = 0; k < 8; k += 2) {
+    const float4 v = *reinterpret_cast<const float4*>(hp + 2 * k);
+    hAP[k] = v.x, hAQ[k] = v.y, hAP[k + 1] = v.z, hAQ[k + 1] = v.w;
+    hBP[k] = 0.0f, hBQ[k] = 0.0f, hBP[k + 1] = 0.0f, hBQ[k + 1] = 0.0f;  // never read: the prologue uses A only
+  }
+  const unsigned char* a0 = blockAddr(ppBegin, 0);
+#pragma unroll
+  for (int e = 0; e < 6; e++) q[e] = *reinterpret_cast<const float4*>(a0 + (unsigned)e * planeBytes);
+#pragma unroll 1
+  for (unsigned pp = ppBegin; pp < ppStop; pp++) {
+    const unsigned char* a1 = blockAddr(pp, 1);
+    firPairBlock<kBlkPrologue, false>(acc, q, hBP, hBQ, hAP, hAQ, a0, a1, planeBytes, hp);
+    a0 = a1;
+    a1 = (pp + 1 < ppStop) ? blockAddr(pp + 1, 0) : a0;
+    firPairBlock<kBlkTail, true>(acc, q, hAP, hAQ, hBP, hBQ, a0, a1, planeBytes, hp + 16);
+    a0 = a1;
+    hp += 16;
   }
 }
 
@@ -697,6 +736,257 @@ __global__ void __launch_bounds__(TG* PSPLIT + 32 * MIXW, MINB)
 #pragma unroll
         for (int r = 0; r < kTmaR; r++) {
           if (ob + r < P.nOut) y[ob + r] = acc[r];
+        }
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Real input x real taps (gsdrFirFF; replaces ref: src/fir.cu:26-71 for <float, float, float>) on the same
+// inner loop.  Two consecutive outputs are one FFMA2 lane pair:
+//     (out[2n], out[2n+1]) = sum_i (x[2n*D + i], x[2n*D + i + D]) * h[i]
+// i.e. a complex-input FIR with decimation 2D over the stream c[k] = (x[k], x[k + D]), whose float2 outputs ARE the
+// real outputs in order.  c is never in HBM: producer warps bulk-copy the raw float window of a tile into shared
+// memory (cp.async.bulk, one instruction per tile, completion on an mbarrier), then rearrange it into the plane
+// layout the FIR loop reads (row m' of c = floats [2D*m', 2D*m' + 3D) of the window).  Filter warps run
+// firComputePairs unchanged.  Hand-over as in the fused-NCO kernel:
+//   rawBar[r]   bytes of raw buffer r have landed                 (tx count, armed by producer thread 0)
+//   fullMix[b]  window b is laid out                              (every producer thread arrives)
+//   empty[b]    the filter warps are done reading window b        (every filter thread arrives)
+// Plane pitch is 16 bytes more than a multiple of 128 so that the eight planes a quarter-warp of producers writes
+// start in eight different bank groups.
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void bulkLoad1d(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smemU32(dst)),
+               "l"(src), "r"(bytes), "r"(smemU32(bar))
+               : "memory");
+}
+
+constexpr unsigned kRealPlanePad = 16;
+
+template <int TG, int PSPLIT, int DT, int MIXW, int NWIN, int NRAW, int MINB>
+__global__ void __launch_bounds__(TG* PSPLIT + 32 * MIXW, MINB) firTmaRealKernel(const RealParams P) {
+  static_assert(NWIN == 1 || NWIN == 2, "one or two window buffers");
+  static_assert(NRAW >= 2 && NRAW <= 4, "raw ring of 2..4 buffers (NRAW-1 bulk copies in flight per CTA)");
+  constexpr unsigned NTF = TG * PSPLIT;  // filter threads
+  constexpr unsigned NTM = 32 * MIXW;    // producer threads
+  constexpr unsigned BOUT = kTmaR * TG;  // output PAIRS per tile
+  extern __shared__ __align__(16) unsigned char smemRaw[];
+  __shared__ __align__(8) unsigned long long rawBar[NRAW], fullMix[2], emptyBar[2];
+  const unsigned D = DT ? (unsigned)DT : P.D;  // pair-stream decimation = 2 x the caller's
+  const unsigned Dr = D >> 1;
+  const unsigned rowBytes = 8u * D;
+  const unsigned segBytes = DT ? tmaSegBytes(DT ? DT : 2) : P.segBytes;
+  const unsigned numSegs = rowBytes / segBytes;
+  const unsigned planeBytes =
+      DT ? tmaPlaneRows(TG, kTmaJpadCap, DT ? DT : 2) * segBytes + kRealPlanePad : P.planeBytes;
+  const unsigned bufBytes = numSegs * 8u * planeBytes;
+  unsigned char* bufBase = smemRaw;
+  float4* scratch = reinterpret_cast<float4*>(bufBase + NWIN * bufBytes);
+  float* hs = reinterpret_cast<float*>(scratch + 2u * (PSPLIT - 1) * (kTmaR / 2) * TG);
+  float* raw = hs + (size_t)D * P.Jpad + 32u;  // NRAW x rawFloats
+
+  const unsigned tid = threadIdx.x;
+  const unsigned rowsStaged = BOUT + P.Jpad;
+  if (tid == 0) {
+    for (int b = 0; b < NRAW; b++) mbarInit(&rawBar[b], 1);
+    for (int b = 0; b < 2; b++) {
+      mbarInit(&fullMix[b], NTM);
+      mbarInit(&emptyBar[b], NTF);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  unsigned chan = blockIdx.x / P.tilesPerChannel;
+  unsigned tile = blockIdx.x - chan * P.tilesPerChannel;
+  // taps -> hs2[pp][j] = (h[j*D + 2pp], h[j*D + 2pp + 1]) by threads [0, nthreads)
+  auto loadTaps = [&](unsigned c, unsigned nthreads) {
+    const float* h = P.h + (size_t)c * P.hStride;
+    const unsigned nh = D * P.Jpad;
+    for (unsigned i = tid; i < nh + 32u; i += nthreads) {
+      const unsigned pp = i / (2u * P.Jpad);
+      const unsigned rem = i - pp * 2u * P.Jpad;
+      const unsigned ti = (rem >> 1) * D + 2u * pp + (rem & 1u);
+      hs[i] = (i < nh && ti < P.T) ? __ldg(h + ti) : 0.0f;
+    }
+  };
+  if (chan < P.numChannels) loadTaps(chan, NTF + NTM);
+  __syncthreads();
+  auto advance = [&](unsigned& c, unsigned& tl) {
+    c += P.strideChan;
+    tl += P.strideTile;
+    if (tl >= P.tilesPerChannel) {
+      tl -= P.tilesPerChannel;
+      c += 1;
+    }
+  };
+
+  if (tid >= NTF) {
+    // ===================== producer warps: raw copy + rearrangement, ahead of the filter warps =====================
+    const unsigned lt = tid - NTF;
+    const float* xr = reinterpret_cast<const float*>(P.x);
+    const unsigned rawBytes = P.rawFloats * 4u;
+    // a tile is bulk-copied when every float it reads lies inside the caller-guaranteed extent
+    auto tileIsFast = [&](unsigned tl) -> bool {
+      return (unsigned long long)tl * BOUT * D + P.rawFloats <= P.nIn;
+    };
+    auto issueRaw = [&](unsigned c, unsigned tl, unsigned rb) {
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      mbarExpectTx(&rawBar[rb], rawBytes);
+      bulkLoad1d(raw + (size_t)rb * P.rawFloats, xr + (size_t)c * P.xStride + (size_t)tl * BOUT * D, rawBytes,
+                 &rawBar[rb]);
+    };
+    // prefetch cursor: the bulk copy of tile k + NRAW - 1 is issued while tile k is rearranged
+    unsigned pfChan = chan, pfTile = tile;
+    for (unsigned j = 0; j + 1 < (unsigned)NRAW; j++) {
+      if (lt == 0 && pfChan < P.numChannels && tileIsFast(pfTile)) issueRaw(pfChan, pfTile, j);
+      if (pfChan < P.numChannels) advance(pfChan, pfTile);
+    }
+    for (unsigned k = 0; chan < P.numChannels; k++) {
+      const unsigned rb = k % NRAW;
+      const unsigned b = (NWIN == 2) ? (k & 1u) : 0u;
+      // ring slot (k - 1) % NRAW was last read one iteration ago (tile k-1); the barrier that ends every iteration
+      // orders those reads before this copy
+      if (lt == 0 && pfChan < P.numChannels && tileIsFast(pfTile)) issueRaw(pfChan, pfTile, (k + NRAW - 1) % NRAW);
+      if (pfChan < P.numChannels) advance(pfChan, pfTile);
+      if (k >= (unsigned)NWIN) mbarWait(&emptyBar[b], ((k / NWIN) - 1u) & 1u);  // filters have left this window
+      float* rawb = raw + (size_t)rb * P.rawFloats;
+      if (tileIsFast(tile)) {
+        mbarWait(&rawBar[rb], (k / NRAW) & 1u);
+      } else {
+        if (lt == 0) mbarArrive(&rawBar[rb]);  // keep the phase of the unused barrier in step with k
+        const float* xc = xr + (size_t)chan * P.xStride;
+        const unsigned long long g0 = (unsigned long long)tile * BOUT * D;
+        for (unsigned i = lt; i < P.rawFloats; i += NTM) {
+          const unsigned long long g = g0 + i;
+          rawb[i] = (g < P.nIn) ? __ldg(xc + g) : 0.0f;
+        }
+        mixBarrier<NTM, 1>();
+      }
+      // rearrange: one work item = one row m' of the pair stream: floats [D*m', D*m' + D + Dr) of the raw window
+      // -> Dr float4 (branch pairs) of plane m' & 7, row group m' >> 3
+      unsigned char* buf = bufBase + b * bufBytes;
+      if (DT == 2) {
+        // decimation 1: rows are (x0, x1, x1, x2) at a stride of two floats; four rows per work item from two
+        // 16-byte loads.  Rows 4q..4q+3 share a row group and sit in planes 4(q & 1) .. 4(q & 1) + 3.
+        for (unsigned q = lt; q < (rowsStaged >> 2); q += NTM) {
+          const float4 a = *reinterpret_cast<const float4*>(rawb + 8u * q);
+          const float4 c = *reinterpret_cast<const float4*>(rawb + 8u * q + 4u);
+          const float e = rawb[8u * q + 8u];
+          unsigned char* dst = buf + ((q & 1u) * 4u) * planeBytes + (q >> 1) * 16u;
+          *reinterpret_cast<float4*>(dst) = make_float4(a.x, a.y, a.y, a.z);
+          *reinterpret_cast<float4*>(dst + planeBytes) = make_float4(a.z, a.w, a.w, c.x);
+          *reinterpret_cast<float4*>(dst + 2u * planeBytes) = make_float4(c.x, c.y, c.y, c.z);
+          *reinterpret_cast<float4*>(dst + 3u * planeBytes) = make_float4(c.z, c.w, c.w, e);
+        }
+      } else
+      for (unsigned m = lt; m < rowsStaged; m += NTM) {
+        const float* r = rawb + (size_t)m * D;
+        unsigned char* rowBase = buf + (m & 7u) * planeBytes;
+        const unsigned mh = m >> 3;
+        if (DT != 0) {
+          // compile-time row: all loads first (8-byte aligned pairs), then the stores
+          constexpr unsigned NF = (DT ? DT : 2) + (DT ? DT : 2) / 2;  // floats read
+          float v[NF + 1];
+#pragma unroll
+          for (unsigned i = 0; i < NF; i += 2) {
+            if (i + 1 < NF) {
+              const float2 t2 = *reinterpret_cast<const float2*>(r + i);
+              v[i] = t2.x;
+              v[i + 1] = t2.y;
+            } else if (i < NF) {
+              v[i] = r[i];
+            }
+          }
+#pragma unroll
+          for (unsigned pp = 0; pp < (DT ? DT : 2) / 2; pp++) {
+            *reinterpret_cast<float4*>(rowBase + tmaPairOffset<DT>(mh, pp, planeBytes, P)) =
+                make_float4(v[2 * pp], v[2 * pp + Dr], v[2 * pp + 1], v[2 * pp + 1 + Dr]);
+          }
+        } else {
+          for (unsigned pp = 0; pp < Dr; pp++) {
+            *reinterpret_cast<float4*>(rowBase + tmaPairOffset<DT>(mh, pp, planeBytes, P)) =
+                make_float4(r[2 * pp], r[2 * pp + Dr], r[2 * pp + 1], r[2 * pp + 1 + Dr]);
+          }
+        }
+      }
+      mbarArrive(&fullMix[b]);  // release: the window is visible to whoever acquires the barrier
+      mixBarrier<NTM, 1>();     // ring slot rb may be overwritten by the copy issued in the next iteration
+      advance(chan, tile);
+    }
+    return;
+  }
+
+  // ============================== filter warps ==============================
+  const unsigned grp = tid / TG;
+  const unsigned t = tid - grp * TG;
+  const unsigned numPairs = D >> 1;
+  const unsigned ppBegin = (grp * numPairs) / PSPLIT;
+  const unsigned ppEnd = ((grp + 1) * numPairs) / PSPLIT;
+  const unsigned long long pairsWhole = P.nOutReal >> 1;  // output pairs with both halves inside the output
+  unsigned tapsChan = chan;
+  for (unsigned k = 0; chan < P.numChannels; k++, advance(chan, tile)) {
+    if (P.hStride != 0 && chan != tapsChan) {
+      // per-channel tap sets: every filter thread has left the previous channel's taps before they are replaced
+      asm volatile("bar.sync 2, %0;" ::"n"(NTF) : "memory");
+      loadTaps(chan, NTF);
+      asm volatile("bar.sync 2, %0;" ::"n"(NTF) : "memory");
+      tapsChan = chan;
+    }
+    const unsigned b = (NWIN == 2) ? (k & 1u) : 0u;
+    const unsigned char* buf = bufBase + b * bufBytes;
+    const unsigned long long o0 = (unsigned long long)tile * BOUT;
+    mbarWait(&fullMix[b], (k / NWIN) & 1u);
+    float2 acc[kTmaR];
+#pragma unroll
+    for (int r = 0; r < kTmaR; r++) acc[r] = make_float2(0.0f, 0.0f);
+    if (ppBegin < ppEnd) {
+      if (P.Jpad == 8u) {
+        firComputePairsShort<DT>(acc, buf, hs, t, ppBegin, ppEnd, planeBytes, P);
+      } else {
+        firComputePairs<DT>(acc, buf, hs, t, ppBegin, ppEnd, P.Jpad, planeBytes, P);
+      }
+    }
+    mbarArrive(&emptyBar[b]);  // this thread has no more reads of the window
+    if (PSPLIT > 1) {
+      float4* red = scratch + (size_t)(k & 1u) * (PSPLIT - 1) * (kTmaR / 2) * TG;
+      if (grp > 0) {
+#pragma unroll
+        for (int q = 0; q < kTmaR / 2; q++) {
+          red[((grp - 1) * (kTmaR / 2) + q) * TG + t] =
+              make_float4(acc[2 * q].x, acc[2 * q].y, acc[2 * q + 1].x, acc[2 * q + 1].y);
+        }
+      }
+      asm volatile("bar.sync 2, %0;" ::"n"(NTF) : "memory");
+      if (grp == 0) {
+#pragma unroll
+        for (int g = 1; g < PSPLIT; g++) {
+#pragma unroll
+          for (int q = 0; q < kTmaR / 2; q++) {
+            const float4 v = red[((g - 1) * (kTmaR / 2) + q) * TG + t];
+            acc[2 * q].x += v.x;
+            acc[2 * q].y += v.y;
+            acc[2 * q + 1].x += v.z;
+            acc[2 * q + 1].y += v.w;
+          }
+        }
+      }
+    }
+    if (grp == 0) {
+      const unsigned long long ob = o0 + (unsigned long long)t * kTmaR;  // first output pair of this thread
+      float* y = reinterpret_cast<float*>(P.y) + (size_t)chan * P.yStride;
+      if (P.y16 && ob + kTmaR <= pairsWhole) {
+#pragma unroll
+        for (int r = 0; r < kTmaR; r += 2) {
+          *reinterpret_cast<float4*>(y + 2 * (ob + r)) = make_float4(acc[r].x, acc[r].y, acc[r + 1].x, acc[r + 1].y);
+        }
+      } else {
+#pragma unroll
+        for (int r = 0; r < kTmaR; r++) {
+          const unsigned long long o = 2 * (ob + r);
+          if (o < P.nOutReal) y[o] = acc[r].x;
+          if (o + 1 < P.nOutReal) y[o + 1] = acc[r].y;
         }
       }
     }

@@ -228,6 +228,31 @@ static constexpr SpecVariant kSpecVariants[] = {
 };
 static constexpr int kNumSpecVariants = (int)(sizeof(kSpecVariants) / sizeof(kSpecVariants[0]));
 
+// Real-input kernel (firTmaRealKernel): X(id, TG, PSPLIT, MIXW, NWIN, NRAW, MINB); ids continue after the fused-NCO
+// variants.  NRAW - 1 bulk copies are in flight per CTA: low-rate (HBM-bound) shapes want 3 or 4.
+#define GSDR_REAL_VARIANTS(X) \
+  X(0, 128, 1, 4, 2, 2, 2)    \
+  X(1, 64, 1, 2, 2, 2, 4)     \
+  X(2, 32, 1, 1, 2, 3, 8)     \
+  X(3, 32, 1, 1, 1, 3, 8)     \
+  X(4, 64, 2, 4, 2, 3, 2)     \
+  X(5, 64, 1, 2, 1, 3, 4)     \
+  X(6, 32, 1, 1, 1, 4, 8)     \
+  X(7, 128, 1, 4, 1, 3, 2)    \
+  X(8, 64, 1, 2, 1, 4, 4)     \
+  X(9, 128, 1, 4, 1, 4, 2)
+
+struct RealVariant {
+  int tg, psplit, mixw, nwin, nraw, minBlocks;
+  int threads() const { return tg * psplit + 32 * mixw; }
+};
+static constexpr RealVariant kRealVariants[] = {
+#define X(id, tg, ps, mw, nw, nr, mb) {tg, ps, mw, nw, nr, mb},
+    GSDR_REAL_VARIANTS(X)
+#undef X
+};
+static constexpr int kNumRealVariants = (int)(sizeof(kRealVariants) / sizeof(kRealVariants[0]));
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -553,6 +578,157 @@ static cudaError_t launchTma(const FirCall& c, int variant, const TmaGeom& geom,
   return cudaErrorInvalidValue;
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Real input (gsdrFirFF) on the TMA kernel's inner loop: firTmaRealKernel
+// ---------------------------------------------------------------------------------------------------------
+struct RealGeom {
+  bool staticD;
+  unsigned Jpad, mhp, planeBytes, swzShift, swzMask, rawFloats;
+  size_t smemBytes;
+};
+
+static bool realStaticDecimation(size_t D2) noexcept { return D2 == 2 || D2 == 10; }
+
+static bool realGeometry(const RealVariant& v, size_t Dreal, size_t T, RealGeom* g) noexcept {
+  const size_t D = 2 * Dreal;  // decimation of the output-pair stream
+  if (!tmaSupportedDecimation(D) || Dreal < (size_t)v.psplit) return false;
+  const size_t J = (T + D - 1) / D;
+  const size_t Jpad = J <= 8 ? 8 : (J + 15) / 16 * 16;
+  const size_t G = tmaSegBytes((unsigned)D);
+  g->staticD = realStaticDecimation(D) && Jpad <= kTmaJpadCap;
+  g->swzShift = 0;
+  g->swzMask = 0;
+  if (G == 32) g->swzShift = 2, g->swzMask = 1;
+  if (G == 64) g->swzShift = 1, g->swzMask = 3;
+  if (G == 128) g->swzShift = 0, g->swzMask = 7;
+  const size_t mhp = tmaPlaneRows((unsigned)v.tg, (unsigned)(g->staticD ? kTmaJpadCap : Jpad), (unsigned)D);
+  const size_t rows = (size_t)kTmaR * v.tg + Jpad;
+  const size_t rawFloats = (rows * D + Dreal + 3) / 4 * 4;
+  if (rawFloats * 4 > 0xfffff0u) return false;  // mbarrier transaction-count range
+  g->Jpad = (unsigned)Jpad;
+  g->mhp = (unsigned)mhp;
+  g->planeBytes = (unsigned)(mhp * G + kRealPlanePad);
+  g->rawFloats = (unsigned)rawFloats;
+  g->smemBytes = (size_t)v.nwin * (8 * D / G) * 8 * (size_t)g->planeBytes + 2 * (size_t)(v.psplit - 1) * v.tg * 64 +
+                 (D * Jpad + 32) * 4 + (size_t)v.nraw * rawFloats * 4;
+  return true;
+}
+
+template <int TG, int PSPLIT, int DT, int MIXW, int NWIN, int NRAW, int MINB>
+static cudaError_t launchRealT(RealParams& P, size_t smem, int dev, int smCount, cudaStream_t stream) noexcept {
+  static std::atomic<size_t> configured[64];
+  auto kernel = firTmaRealKernel<TG, PSPLIT, DT, MIXW, NWIN, NRAW, MINB>;
+  constexpr int kThreads = TG * PSPLIT + 32 * MIXW;
+  if (smem > configured[dev & 63].load(std::memory_order_acquire)) {
+    cudaError_t st = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (st != cudaSuccess) return report(st, "cudaFuncSetAttribute(MaxDynamicSharedMemorySize)");
+    configured[dev & 63].store(smem, std::memory_order_release);
+  }
+  int perSm = 0;
+  cudaError_t st = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, kernel, kThreads, smem);
+  if (st != cudaSuccess) return report(st, "cudaOccupancyMaxActiveBlocksPerMultiprocessor");
+  if (perSm < 1) return cudaErrorInvalidConfiguration;
+  {
+    const int warpsPerCta = kThreads / 32;
+    int balanced = perSm;
+    while (balanced > 1 && (balanced * warpsPerCta) % 4 != 0) balanced--;
+    if ((balanced * warpsPerCta) % 4 == 0) perSm = balanced;
+  }
+  const unsigned long long resident = (unsigned long long)perSm * (unsigned)smCount;
+  const unsigned grid = (unsigned)(P.totalTiles < resident ? P.totalTiles : resident);
+  P.strideChan = grid / P.tilesPerChannel;
+  P.strideTile = grid % P.tilesPerChannel;
+  void* args[] = {(void*)&P};
+  return cudaLaunchKernel((const void*)kernel, dim3(grid), dim3(kThreads), args, smem, stream);
+}
+
+template <int DT>
+static cudaError_t launchRealD(int variant, RealParams& P, size_t smem, int dev, int smCount,
+                               cudaStream_t stream) noexcept {
+  switch (variant) {
+#define X(id, tg, ps, mw, nw, nr, mb) \
+  case id: return launchRealT<tg, ps, DT, mw, nw, nr, mb>(P, smem, dev, smCount, stream);
+    GSDR_REAL_VARIANTS(X)
+#undef X
+    default: return cudaErrorInvalidValue;
+  }
+}
+
+static bool realVariantFits(int id, const FirCall& c, int maxSmem, RealGeom* geom) noexcept {
+  if (id < 0 || id >= kNumRealVariants) return false;
+  return realGeometry(kRealVariants[id], c.decimation, c.tapCount, geom) && geom->smemBytes <= (size_t)maxSmem;
+}
+
+// Returns the real-input variant for this call, or -1 when the call does not qualify.
+static int chooseRealVariant(const FirCall& c, int maxSmem, RealGeom* geom) noexcept {
+  if (c.type != kFirFF || c.nco != kNcoNone) return -1;
+  if (!tmaSupportedDecimation(2 * c.decimation)) return -1;
+  if ((uintptr_t)c.input % 16 != 0) return -1;                    // bulk copies need a 16-byte aligned source
+  if (c.numChannels > 1 && (c.inputStride % 4) != 0) return -1;   // ... in every channel
+  if (c.numChannels > 0x7fffffffull) return -1;
+  const int firstId = kNumVariants + kNumTmaVariants + kNumSpecVariants;
+  const int forced = gForcedVariant.load(std::memory_order_relaxed);
+  if (forced >= firstId) return realVariantFits(forced - firstId, c, maxSmem, geom) ? forced - firstId : -1;
+  if (forced != -1) return -1;
+  // one branch pair (decimation 1): four filter warps + four producer warps; more pairs: smaller tiles, more CTAs
+  // (tools/sweep.py --kind ff: D = 1 -> id 0 at 0.209 ms for 2^26 samples x 63 taps, D = 5 -> id 7 at 0.217 ms for 2^27)
+  static const int orderOnePair[] = {0, 1, 2, 3};
+  static const int orderMore[] = {7, 5, 4, 1};
+  const int* order = c.decimation == 1 ? orderOnePair : orderMore;
+  for (int k = 0; k < 4; k++) {
+    RealGeom g;
+    if (realVariantFits(order[k], c, maxSmem, &g)) {
+      *geom = g;
+      return order[k];
+    }
+  }
+  return -1;
+}
+
+static cudaError_t launchReal(const FirCall& c, int variant, const RealGeom& geom, int dev, int smCount,
+                              cudaStream_t stream) noexcept {
+  const RealVariant& v = kRealVariants[variant];
+  const size_t bout = (size_t)kTmaR * v.tg;                      // output pairs per tile
+  const unsigned long long pairs = (c.numOutputs + 1) / 2;
+  const unsigned long long tiles = (pairs + bout - 1) / bout;
+  const unsigned long long total = tiles * c.numChannels;
+  if (tiles > 0x7fffffffull || total > 0x7fffffffull) return cudaErrorInvalidValue;
+  const size_t D = 2 * c.decimation;
+  RealParams P{};
+  P.x = (const float2*)c.input;
+  P.h = (const float*)c.taps;
+  P.y = (float2*)c.output;
+  P.nOut = pairs;
+  P.nOutReal = c.numOutputs;
+  P.nIn = (unsigned long long)(c.numOutputs - 1) * c.decimation + c.tapCount;  // floats
+  P.xStride = c.inputStride;
+  P.yStride = c.outputStride;
+  P.hStride = c.tapStride;
+  P.tilesPerChannel = (unsigned)tiles;
+  P.totalTiles = (unsigned)total;
+  P.numChannels = (unsigned)c.numChannels;
+  P.D = (unsigned)D;
+  P.T = (unsigned)c.tapCount;
+  P.Jpad = geom.Jpad;
+  P.rowBytes = (unsigned)(8 * D);
+  P.segBytes = tmaSegBytes((unsigned)D);
+  P.mhp = geom.mhp;
+  P.planeBytes = geom.planeBytes;
+  P.swzShift = geom.swzShift;
+  P.swzMask = geom.swzMask;
+  P.rawFloats = geom.rawFloats;
+  P.y16 = ((uintptr_t)c.output % 16 == 0 && (c.numChannels == 1 || (c.outputStride * 4) % 16 == 0)) ? 1u : 0u;
+  P.dbg = (unsigned)gDebugFlags.load(std::memory_order_relaxed);
+  if (geom.staticD) {
+    switch (D) {
+      case 2: return launchRealD<2>(variant, P, geom.smemBytes, dev, smCount, stream);
+      case 10: return launchRealD<10>(variant, P, geom.smemBytes, dev, smCount, stream);
+      default: break;
+    }
+  }
+  return launchRealD<0>(variant, P, geom.smemBytes, dev, smCount, stream);
+}
+
 template <class IN_T, class OUT_T, class TAP_T>
 static cudaError_t launchDirect(const FirCall& c, cudaStream_t stream) noexcept {
   DirectParams P;
@@ -599,6 +775,9 @@ cudaError_t enqueueFir(const FirCall& c, cudaStream_t stream) noexcept {
     TmaGeom tg{};
     const int tv = chooseTmaVariant(c, info->maxSmemOptin, &tg);
     if (tv >= 0) return launchTma(c, tv, tg, dev, info->smCount, stream);
+    RealGeom rg{};
+    const int rv = chooseRealVariant(c, info->maxSmemOptin, &rg);
+    if (rv >= 0) return launchReal(c, rv, rg, dev, info->smCount, stream);
   }
   const bool polyType = (c.type == kFirFC || c.type == kFirFF);
   PolyGeom geom{};
@@ -751,13 +930,13 @@ GSDR_C_LINKAGE uint64_t gsdrNcoPhaseStep(float frequencyShift, float sampleRate)
 // ---- tuning / introspection hooks of <gsdr/b200.h> -------------------------------------------------------
 
 GSDR_C_LINKAGE int gsdrB200SetKernelVariant(int variant) GSDR_NO_EXCEPT {
-  if (variant < -2 || variant >= kNumVariants + kNumTmaVariants + kNumSpecVariants) return -1;
+  if (variant < -2 || variant >= kNumVariants + kNumTmaVariants + kNumSpecVariants + kNumRealVariants) return -1;
   gForcedVariant.store(variant, std::memory_order_relaxed);
   return 0;
 }
 
 GSDR_C_LINKAGE int gsdrB200NumKernelVariants(void) GSDR_NO_EXCEPT {
-  return kNumVariants + kNumTmaVariants + kNumSpecVariants;
+  return kNumVariants + kNumTmaVariants + kNumSpecVariants + kNumRealVariants;
 }
 GSDR_C_LINKAGE int gsdrB200NumPolyphaseVariants(void) GSDR_NO_EXCEPT { return kNumVariants; }
 
@@ -799,6 +978,28 @@ GSDR_C_LINKAGE int gsdrB200DescribeKernel(int firType, size_t decimation, size_t
       info->windowBuffers = vs.nbuf;
       info->outputsPerBlock = bout;
       info->sharedBytesPerBlock = tg.smemBytes;
+      info->numBlocks = (numOutputs + bout - 1) / bout;
+      return 0;
+    }
+  }
+  if (firType == kFirFF) {
+    FirCall probe;
+    probe.type = kFirFF;
+    probe.decimation = decimation;
+    probe.tapCount = tapCount;
+    probe.numOutputs = numOutputs;
+    RealGeom rg{};
+    const int rv = chooseRealVariant(probe, di->maxSmemOptin, &rg);
+    if (rv >= 0) {
+      const RealVariant& vs = kRealVariants[rv];
+      const size_t bout = 2 * (size_t)kTmaR * vs.tg;
+      info->variant = kNumVariants + kNumTmaVariants + kNumSpecVariants + rv;
+      info->outputsPerThread = 2 * kTmaR;
+      info->threadsPerBlock = vs.threads();
+      info->phaseGroups = vs.psplit;
+      info->windowBuffers = vs.nwin;
+      info->outputsPerBlock = bout;
+      info->sharedBytesPerBlock = rg.smemBytes;
       info->numBlocks = (numOutputs + bout - 1) / bout;
       return 0;
     }

@@ -90,7 +90,8 @@ def test_polyphase_against_oracle(kind, D, T, n_in, cuda_device):
         assert np.abs(y.astype(truth.dtype) - truth).max() <= _tol(taps, x)
 
 
-N_POLY, N_TMA, N_ALL = 12, 24, 30  # polyphase (cp.async), TMA-fed, warp-specialised fused-NCO variants
+# polyphase (cp.async) | TMA-fed | warp-specialised fused NCO | real-input variants
+N_POLY, N_TMA, N_SPEC, N_ALL = 12, 24, 30, 40
 
 
 @pytest.mark.parametrize("variant", [-2] + list(range(N_ALL)))
@@ -103,11 +104,13 @@ def test_every_kernel_variant(kind, variant, cuda_device):
     n_out = g.fir_num_outputs(n_in, T, D) - 3  # ragged: last tile partly filled, input longer than needed
     g.set_kernel_variant(variant)
     info = g.describe_kernel(0 if kind == "fc" else 1, D, T, n_out)
-    tma_only_fc = variant >= N_POLY and kind == "ff"  # the TMA kernel is complex-input only
+    wrong_type = (N_POLY <= variant < N_SPEC and kind == "ff") or (variant >= N_SPEC and kind == "fc")
     if variant >= N_POLY and kind == "fc" and info.variant == -1:
         assert info.phaseGroups <= 1  # e.g. 8 branch groups requested but D = 8 has only 4 branch pairs
+    elif variant >= N_SPEC and kind == "ff" and info.variant == -1:
+        pass  # a real-input variant whose window does not fit this shape (128-byte rows x 1024 outputs)
     else:
-        assert info.variant == (variant if variant >= 0 and not tma_only_fc else -1)
+        assert info.variant == (variant if variant >= 0 and not wrong_type else -1)
     y = _run(kind, D, taps, x, n_out, cuda_device)
     want = oracle.fir(kind, D, taps, x, n_out)
     if info.variant == -1:
@@ -116,7 +119,63 @@ def test_every_kernel_variant(kind, variant, cuda_device):
         assert np.abs(y - want).max() <= _tol(taps, x)
 
 
-@pytest.mark.parametrize("variant", list(range(N_POLY, N_ALL)))
+@pytest.mark.parametrize("variant", list(range(N_SPEC, N_ALL)))
+@pytest.mark.parametrize("D,T,n_out", [(1, 63, 70_001), (1, 7, 5000), (2, 100, 40_000), (3, 17, 33_333), (4, 127, 30_001),
+                                       (5, 63, 50_001), (5, 200, 20_000), (7, 29, 9_999), (8, 255, 20_000),
+                                       (16, 1023, 9_000), (64, 300, 2_001)])
+def test_real_input_kernel(variant, D, T, n_out, cuda_device):
+    """gsdrFirFF on the output-pair kernel: pairs of consecutive outputs share an FFMA2, producer warps rearrange the
+    bulk-copied raw window.  Odd output counts (half-filled last pair), one tap block (T <= 16 D) and several,
+    interior tiles (bulk copy) and the last ones (bounds-checked loads) all occur."""
+    taps = synth.random_taps(T, 9 + D)
+    x = synth.tone_plus_noise(0, (n_out - 1) * D + T, seed=90 + D, real=True)
+    g.set_kernel_variant(variant)
+    info = g.describe_kernel(1, D, T, n_out)
+    if info.variant == -1:
+        pytest.skip("variant does not fit this shape")
+    assert info.variant == variant
+    dt, dx = torch.from_numpy(taps).to(cuda_device), torch.from_numpy(x).to(cuda_device)
+    dy = torch.full((n_out + 8,), 7.0, dtype=torch.float32, device=cuda_device)
+    g.gsdrFirFF(D, dt, T, dx, dy, n_out, 0, None)
+    torch.cuda.synchronize()
+    y = dy.cpu().numpy()
+    assert (y[n_out:] == 7.0).all(), "wrote past the last output"
+    want = oracle.fir("ff", D, taps, x, n_out, threads=8)
+    assert np.abs(y[:n_out] - want).max() <= _tol(taps, x)
+    # unaligned output (4-byte aligned only): scalar store path
+    dy2 = torch.zeros(n_out + 1, dtype=torch.float32, device=cuda_device)
+    g.gsdrFirFF(D, dt, T, dx, dy2[1:], n_out, 0, None)
+    torch.cuda.synchronize()
+    assert dy2[1:].cpu().numpy().tobytes() == y[:n_out].tobytes()
+
+
+def test_real_input_batched_and_unaligned(cuda_device):
+    """Channel batches go through the same kernel (channel = part of the tile index); inputs that are not 16-byte
+    aligned fall back to the cp.async kernel and still match."""
+    D, T, n_out, C = 5, 63, 12_345, 7
+    taps = synth.random_taps(T, 3)
+    n_in = (n_out - 1) * D + T
+    stride_in = (n_in + 3) // 4 * 4
+    xs = np.stack([np.pad(synth.tone_plus_noise(c, n_in, seed=70 + c, real=True), (0, stride_in - n_in)) for c in range(C)])
+    dt, dx = torch.from_numpy(taps).to(cuda_device), torch.from_numpy(xs).to(cuda_device)
+    dy = torch.zeros((C, n_out + 3), dtype=torch.float32, device=cuda_device)
+    g.gsdrFirFFBatched(D, dt, T, 0, dx, stride_in, dy, n_out + 3, n_out, C, 0, None)
+    torch.cuda.synchronize()
+    for c in range(C):
+        want = oracle.fir("ff", D, taps, xs[c, :n_in], n_out)
+        assert np.abs(dy[c, :n_out].cpu().numpy() - want).max() <= _tol(taps, xs[c])
+    one = torch.zeros(n_out, dtype=torch.float32, device=cuda_device)
+    g.gsdrFirFF(D, dt, T, dx[3], one, n_out, 0, None)
+    torch.cuda.synchronize()
+    assert one.cpu().numpy().tobytes() == dy[3, :n_out].cpu().numpy().tobytes(), "batched == single call, bit for bit"
+    xo = torch.from_numpy(np.concatenate([np.zeros(1, np.float32), xs[0]])).to(cuda_device)
+    g.gsdrFirFF(D, dt, T, xo[1:], one, n_out, 0, None)  # 4-byte aligned input
+    torch.cuda.synchronize()
+    want = oracle.fir("ff", D, taps, xs[0, :n_in], n_out)
+    assert np.abs(one.cpu().numpy() - want).max() <= _tol(taps, xs[0])
+
+
+@pytest.mark.parametrize("variant", list(range(N_POLY, N_SPEC)))
 @pytest.mark.timeout(120)
 @pytest.mark.parametrize("D,T", [(2, 33), (4, 127), (6, 100), (8, 255), (10, 255), (14, 29), (16, 500), (32, 1023), (48, 700), (64, 129)])
 def test_tma_kernel_decimations_and_swizzle_modes(variant, D, T, cuda_device):
