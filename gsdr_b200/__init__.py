@@ -6,6 +6,7 @@ order and meaning as the reference's `include/gsdr/fir.h`, with torch tensors st
 """
 from .api import (  # noqa: F401
     CudaError,
+    FirStream,
     HostPipeline,
     describe_kernel,
     fir_num_inputs,
@@ -27,6 +28,7 @@ from .api import (  # noqa: F401
     num_polyphase_variants,
     shard_plan_channels,
     shard_plan_time,
+    stream_plan,
 )
 
 __all__ = [n for n in dir() if not n.startswith("_")]

@@ -1,7 +1,7 @@
-"""ctypes binding of libgsdr_b200.so — the C ABI declared in include/gsdr/{fir,adjust_frequency,b200}.h.
+"""ctypes binding of libgsdr_b200.so — the C ABI declared in include/gsdr/*.h.
 
 There is deliberately no fallback: if the shared library is missing or a symbol cannot be resolved, importing
-this module raises.  (Use `python -m gsdr_b200.build` or `__graft_entry__.build()` to compile it.)
+this module raises.  (Use `python gsdr_b200/build.py` or `__graft_entry__.build()` to compile it.)
 """
 from __future__ import annotations
 
@@ -27,6 +27,13 @@ class Shard(C.Structure):
         ("numInputs", C.c_uint64),
         ("firstSampleIndex", C.c_uint64),
     ]
+
+
+class StreamPlan(C.Structure):
+    """gsdrStreamPlan of include/gsdr/stream.h."""
+
+    _fields_ = [(n, C.c_uint64) for n in ("numOutputs", "skippedInputs", "headOutputs", "headNewInputs", "bodyOutputs",
+                                         "bodyOffset", "carryLength", "newCarryLength", "newNextStart")]
 
 
 class KernelInfo(C.Structure):
@@ -83,6 +90,15 @@ SIGNATURES = {
                                                    c_void_p, c_void_p, c_size_t]),
     "gsdrFirFCMultiGpuHost": (cudaError_t, [C.POINTER(c_void_p), C.c_int, c_size_t, c_void_p, c_size_t, c_void_p,
                                             c_void_p, c_size_t]),
+    # include/gsdr/stream.h
+    "gsdrFirStreamPlan": (C.c_int, [C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint32,
+                                    C.POINTER(StreamPlan)]),
+    "gsdrFirStreamCreate": (cudaError_t, [C.POINTER(c_void_p), C.c_int, c_size_t, c_void_p, c_size_t, c_float, c_float,
+                                          c_size_t, c_int32]),
+    "gsdrFirStreamDestroy": (None, [c_void_p]),
+    "gsdrFirStreamReset": (None, [c_void_p]),
+    "gsdrFirStreamNumOutputs": (c_size_t, [c_void_p, c_size_t]),
+    "gsdrFirStreamPush": (cudaError_t, [c_void_p, c_void_p, c_size_t, c_void_p, C.POINTER(c_size_t), c_void_p]),
     "gsdrB200DescribeKernel": (C.c_int, [C.c_int, c_size_t, c_size_t, c_size_t, c_int32, C.POINTER(KernelInfo)]),
     "gsdrB200SetKernelVariant": (C.c_int, [C.c_int]),
     "gsdrB200NumKernelVariants": (C.c_int, []),
@@ -94,7 +110,7 @@ SIGNATURES = {
 def _load() -> C.CDLL:
     if not LIB_PATH.exists():
         raise ImportError(
-            f"{LIB_PATH} is missing: the CUDA library has not been built (run `python -m gsdr_b200.build`). "
+            f"{LIB_PATH} is missing: the CUDA library has not been built (run `python gsdr_b200/build.py`). "
             "gsdr_b200 has no CPU fallback.")
     lib = C.CDLL(str(LIB_PATH))
     for name, (res, args) in SIGNATURES.items():

@@ -11,7 +11,7 @@ from __future__ import annotations
 import ctypes as C
 from typing import Optional
 
-from ._lib import KernelInfo, Shard, lib
+from ._lib import KernelInfo, Shard, StreamPlan, lib
 
 
 class CudaError(RuntimeError):
@@ -194,3 +194,44 @@ class HostPipeline:
         _check(lib.gsdrAdjustFrequencyFirFCHost(self._h, sampleRate, frequencyShift, firstSampleIndex, decimation,
                                                 _ptr(taps), tapCount, _ptr(input), _ptr(output), numOutputs),
                "gsdrAdjustFrequencyFirFCHost")
+
+
+def stream_plan(decimation, tapCount, totalInputs, nextStart, numInputs, align=2) -> StreamPlan:
+    p = StreamPlan()
+    if lib.gsdrFirStreamPlan(decimation, tapCount, totalInputs, nextStart, numInputs, align, C.byref(p)) != 0:
+        raise ValueError("gsdrFirStreamPlan: invalid arguments")
+    return p
+
+
+class FirStream:
+    """gsdrFirStream: feed blocks of any length; the concatenated outputs equal one call over the whole input."""
+
+    FC, FF, FC_NCO = 0, 1, 4
+
+    def __init__(self, firType, decimation, taps, tapCount, sampleRate=0.0, frequencyShift=0.0, firstSampleIndex=0,
+                 cudaDevice=0):
+        h = C.c_void_p()
+        _check(lib.gsdrFirStreamCreate(C.byref(h), firType, decimation, _ptr(taps), tapCount, sampleRate,
+                                       frequencyShift, firstSampleIndex, cudaDevice), "gsdrFirStreamCreate")
+        self._h: Optional[C.c_void_p] = h
+
+    def close(self) -> None:
+        if self._h is not None:
+            lib.gsdrFirStreamDestroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        self.close()
+
+    def reset(self) -> None:
+        lib.gsdrFirStreamReset(self._h)
+
+    def num_outputs(self, numInputs: int) -> int:
+        return int(lib.gsdrFirStreamNumOutputs(self._h, numInputs))
+
+    def push(self, input, numInputs, output, cudaStream=None) -> int:
+        n = C.c_size_t(0)
+        _check(lib.gsdrFirStreamPush(self._h, _ptr(input) if numInputs else None, numInputs,
+                                     _ptr(output) if output is not None else None, C.byref(n), _stream(cudaStream)),
+               "gsdrFirStreamPush")
+        return int(n.value)

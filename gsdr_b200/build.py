@@ -15,7 +15,7 @@ from pathlib import Path
 ROOT = Path(__file__).resolve().parent.parent
 CSRC = ROOT / "gsdr_b200" / "csrc"
 LIB = CSRC / "libgsdr_b200.so"
-SOURCES = [CSRC / "gsdr_fir.cu", CSRC / "gsdr_host.cu", CSRC / "gsdr_demod.cu"]
+SOURCES = [CSRC / "gsdr_fir.cu", CSRC / "gsdr_host.cu", CSRC / "gsdr_demod.cu", CSRC / "gsdr_stream.cu"]
 HEADERS = sorted(CSRC.glob("*.cuh")) + sorted(CSRC.glob("*.h")) + sorted((ROOT / "include" / "gsdr").glob("*.h"))
 
 NVCC_FLAGS = [

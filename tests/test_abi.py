@@ -57,7 +57,7 @@ def test_headers_compile_as_c_and_cxx(tmp_path):
     cuda_inc = "/usr/local/cuda/include"
     if not Path(cuda_inc, "cuda_runtime.h").exists():
         pytest.skip("CUDA headers not installed")
-    src = '#include <gsdr/fir.h>\n#include <gsdr/adjust_frequency.h>\n#include <gsdr/b200.h>\nint main(void){return 0;}\n'
+    src = ''.join(f'#include <gsdr/{h.name}>\n' for h in sorted(INCLUDE.glob('*.h'))) + 'int main(void){return 0;}\n'
     for compiler, name in (("gcc", "t.c"), ("g++", "t.cpp")):
         f = tmp_path / name
         f.write_text(src)
