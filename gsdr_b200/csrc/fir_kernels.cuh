@@ -506,4 +506,61 @@ __global__ void __launch_bounds__(kDirectThreads) firDirectKernel(const DirectPa
   if (live) reinterpret_cast<OUT_T*>(P.y)[(size_t)chan * P.yStride + n] = acc;
 }
 
+// Direct kernel with the NCO mix-down in front of every tap (any D / T): the fallback for shapes whose window does
+// not fit the staged kernels.  One sincospi per tap per output — T/D times more phasor work than the staged kernels,
+// which mix every input sample once — but no shared-memory limit.  Same phase laws as mixWindow().
+struct DirectNcoParams {
+  const float2* x;
+  const float* h;
+  float2* y;
+  unsigned long long nOut, D, T;
+  unsigned long long xStride, yStride, hStride;
+  unsigned blocksPerChannel;
+  unsigned long long ncoStep, ncoFirst;
+  unsigned ncoFirst32;
+  float ncoFs, ncoF;
+};
+
+template <int MODE>
+__global__ void __launch_bounds__(kDirectThreads) firDirectNcoKernel(const DirectNcoParams P) {
+  __shared__ float hs[kDirectTapChunk];
+  const unsigned chan = blockIdx.x / P.blocksPerChannel;
+  const unsigned blk = blockIdx.x - chan * P.blocksPerChannel;
+  const unsigned long long n = (unsigned long long)blk * kDirectThreads + threadIdx.x;
+  const bool live = n < P.nOut;
+  const unsigned long long s0 = live ? n * P.D : 0ull;  // index of the window's first sample, relative to input[0]
+  const float2* x = P.x + (size_t)chan * P.xStride + s0;
+  const float* h = P.h + (size_t)chan * P.hStride;
+  float2 acc = make_float2(0.0f, 0.0f);
+  for (unsigned long long t0 = 0; t0 < P.T; t0 += kDirectTapChunk) {
+    const unsigned cnt = (unsigned)((P.T - t0 < (unsigned long long)kDirectTapChunk) ? (P.T - t0) : kDirectTapChunk);
+    __syncthreads();
+    for (unsigned i = threadIdx.x; i < cnt; i += kDirectThreads) hs[i] = h[t0 + i];
+    __syncthreads();
+    if (live) {
+      const float2* xp = x + t0;
+      unsigned long long phase = (P.ncoFirst + s0 + t0) * P.ncoStep;  // mod 2^64
+      for (unsigned i = 0; i < cnt; i++) {
+        float sn, cs;
+        if (MODE == kPolyNcoExact) {
+          sincospif((float)(int)(unsigned)(phase >> 32) * 4.656612873077392578125e-10f, &sn, &cs);
+          phase += P.ncoStep;
+        } else {
+          // ref: src/adjustFrequency.cu:23,35-50, with the uint32 wrap of ref: src/fm.cu:43-47
+          const unsigned idx = P.ncoFirst32 + (unsigned)(s0 + t0 + i);
+          const float period = __frcp_rn(P.ncoF);
+          const float tt = __fdiv_rn(fmodf(__uint2float_rn(idx), P.ncoFs), P.ncoFs);
+          sincospif(fmodf(tt, period) * 2.0f, &sn, &cs);
+        }
+        const float2 v = __ldg(xp + i);
+        const float mre = __fmaf_rn(v.x, cs, -__fmul_rn(v.y, sn));
+        const float mim = __fmaf_rn(v.x, sn, __fmul_rn(v.y, cs));
+        acc.x = __fmaf_rn(hs[i], mre, acc.x);
+        acc.y = __fmaf_rn(hs[i], mim, acc.y);
+      }
+    }
+  }
+  if (live) P.y[(size_t)chan * P.yStride + n] = acc;
+}
+
 }  // namespace gsdr_b200

@@ -750,6 +750,32 @@ static cudaError_t launchDirect(const FirCall& c, cudaStream_t stream) noexcept 
                           dim3(kDirectThreads), args, 0, stream);
 }
 
+static cudaError_t launchDirectNco(const FirCall& c, cudaStream_t stream) noexcept {
+  DirectNcoParams P{};
+  P.x = (const float2*)c.input;
+  P.h = (const float*)c.taps;
+  P.y = (float2*)c.output;
+  P.nOut = c.numOutputs;
+  P.D = c.decimation;
+  P.T = c.tapCount;
+  P.xStride = c.inputStride;
+  P.yStride = c.outputStride;
+  P.hStride = c.tapStride;
+  const unsigned long long bpc = (c.numOutputs + kDirectThreads - 1) / kDirectThreads;
+  const unsigned long long grid = bpc * c.numChannels;
+  if (bpc > 0x7fffffffull || grid > 0x7fffffffull) return cudaErrorInvalidValue;
+  P.blocksPerChannel = (unsigned)bpc;
+  P.ncoStep = ncoPhaseStep(c.frequencyShift, c.sampleRate);
+  P.ncoFirst = c.firstSampleIndex;
+  P.ncoFirst32 = (uint32_t)fmodf((float)c.firstSampleIndex, c.sampleRate);  // ref: src/fm.cu:202
+  P.ncoFs = c.sampleRate;
+  P.ncoF = c.frequencyShift;
+  void* args[] = {(void*)&P};
+  const void* kernel = c.nco == kNcoExact ? (const void*)firDirectNcoKernel<kPolyNcoExact>
+                                          : (const void*)firDirectNcoKernel<kPolyNcoLiteral>;
+  return cudaLaunchKernel(kernel, dim3((unsigned)grid), dim3(kDirectThreads), args, 0, stream);
+}
+
 static size_t outElemBytes(FirType t) noexcept { return t == kFirFF ? 4 : 8; }
 
 cudaError_t enqueueFir(const FirCall& c, cudaStream_t stream) noexcept {
@@ -783,7 +809,7 @@ cudaError_t enqueueFir(const FirCall& c, cudaStream_t stream) noexcept {
   PolyGeom geom{};
   const int variant = polyType ? choosePolyVariant(c.decimation, c.tapCount, c.numOutputs, info->maxSmemOptin, &geom) : -1;
   if (variant < 0) {
-    if (c.nco != kNcoNone) return cudaErrorInvalidValue;  // TODO(round 2): phase-chunked kernel for huge D*T
+    if (c.nco != kNcoNone) return launchDirectNco(c, stream);
     switch (c.type) {
       case kFirFC: return launchDirect<float2, float2, float>(c, stream);
       case kFirFF: return launchDirect<float, float, float>(c, stream);

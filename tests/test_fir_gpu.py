@@ -386,6 +386,28 @@ def test_nco_literal_against_oracle(first, cuda_device):
     assert np.abs(dy.cpu().numpy() - want).max() <= _tol(taps, x)
 
 
+@pytest.mark.parametrize("literal", [False, True])
+@pytest.mark.parametrize("D,T,n_out,forced", [(100, 400, 3000, -1), (4096, 70, 500, -1), (131, 5000, 700, -1),
+                                              (8, 255, 5000, -2)])
+def test_nco_direct_fallback(D, T, n_out, forced, literal, cuda_device):
+    """Shapes whose window fits no staged kernel (large decimations that are not a multiple of 16, very long tap
+    sets) take the direct NCO kernel — one phasor per tap per output — instead of failing."""
+    fs, f, first = 2.4e6, 1.0e5, 2 ** 34 + 5 if not literal else 1_000_003
+    taps = synth.random_taps(T, 21)
+    x = synth.tone_plus_noise(0, (n_out - 1) * D + T, seed=38)
+    dt, dx = torch.from_numpy(taps).to(cuda_device), torch.from_numpy(x).to(cuda_device)
+    dy = torch.zeros(n_out, dtype=torch.complex64, device=cuda_device)
+    g.set_kernel_variant(forced)
+    assert g.describe_kernel(4, D, T, n_out).variant == -1
+    fn = g.gsdrAdjustFrequencyFirFCLiteral if literal else g.gsdrAdjustFrequencyFirFC
+    fn(fs, f, first, D, dt, T, dx, dy, n_out, 0, None)
+    torch.cuda.synchronize()
+    mode = oracle.NCO_LITERAL if literal else oracle.NCO_EXACT
+    n_chk = min(n_out, 600)
+    want = oracle.adjust_frequency_fir_fc(mode, fs, f, first, D, taps, x, n_chk, f64=not literal)
+    assert np.abs(dy[:n_chk].cpu().numpy() - want).max() <= _tol(taps, x)
+
+
 # ---- against the reference's own CUDA kernels (oracle/_ref) ------------------------------------------------
 
 needs_ref = pytest.mark.skipif(not ref_cuda.available(), reason="oracle/_ref/libgsdr_ref.so not built")
