@@ -6,9 +6,11 @@ this module raises.  (Use `python gsdr_b200/build.py` or `__graft_entry__.build(
 from __future__ import annotations
 
 import ctypes as C
+import os
 from pathlib import Path
 
-LIB_PATH = Path(__file__).resolve().parent / "csrc" / "libgsdr_b200.so"
+# GSDR_B200_LIB: development hook (tools/exp_build.py) to load an experimental build of the same library
+LIB_PATH = Path(os.environ.get("GSDR_B200_LIB") or Path(__file__).resolve().parent / "csrc" / "libgsdr_b200.so")
 
 c_size_t = C.c_size_t
 c_void_p = C.c_void_p

@@ -23,7 +23,13 @@ NVCC_FLAGS = [
     "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC,-fvisibility=hidden",
     "-Xptxas", "-v",
-    "-split-compile", "0",  # ptxas over all host cores: ~150 template instantiations of the big kernels
+    # Take the register-hungry schedule of the FIR loop (135 registers instead of 127: +2.5 % on the headline shape;
+    # residency is bound by shared memory, not registers).
+    "-Xptxas", "--register-usage-level=10",
+    # ptxas (only) over all host cores: ~300 template instantiations of the big kernels.  NOT nvcc's own
+    # -split-compile: that also splits the module inside the NVVM optimiser, and the FIR loop then comes out in one
+    # of two schedules (98 or 126 registers, 7 % apart) depending on unrelated source changes (profiles/r01_notes.md).
+    "-Xptxas", "--split-compile=0",
 ]
 
 

@@ -145,6 +145,13 @@ __device__ __forceinline__ void tmaLoad4(void* dst, const CUtensorMap* map, unsi
 
 enum TmaBlockKind : int { kBlkPrologue = 0, kBlkSteady = 1, kBlkTail = 2 };
 
+// Elements the sample ring runs ahead of the FFMA2s (ring of 8 slots: 1..8).  Tuning knob, see profiles/r01_notes.md.
+#ifndef GSDR_TMA_LOOKAHEAD
+#define GSDR_TMA_LOOKAHEAD 6
+#endif
+constexpr int kTmaAhead = GSDR_TMA_LOOKAHEAD;
+static_assert(kTmaAhead >= 1 && kTmaAhead <= 8, "the sample ring has 8 slots");
+
 // One block of 8 window elements of a branch pair.  q[]: sample ring (slot = element index & 7).
 // hnP/hnQ: taps block b ("new") of branches P/Q, hoP/hoQ: taps block b-1 ("old").  Element i feeds output r with
 // tap (i-r) of the new block when r <= i, with tap (8+i-r) of the old block when r > i.  After element i its ring
@@ -177,9 +184,9 @@ __device__ __forceinline__ void firPairBlock(
         }
       }
     }
-    // sample six elements ahead -> the ring slot that element (i-2) vacated
+    // sample kTmaAhead (six) elements ahead -> the ring slot that element (i-2) vacated
     {
-      const int e = i + 6;
+      const int e = i + kTmaAhead;
       const bool skip = (KIND == kBlkTail && e == 7);  // element 7 of the tail block is never used
       if (!skip) {
         const unsigned char* addr = (e < 8) ? a0 + (unsigned)e * planeBytes : a1 + (unsigned)(e - 8) * planeBytes;
@@ -340,7 +347,7 @@ __device__ __forceinline__ void firComputePairs(float2 (&acc)[kTmaR], const unsi
   }
   const unsigned char* a0 = blockAddr(ppBegin, 0);
 #pragma unroll
-  for (int e = 0; e < 6; e++) q[e] = *reinterpret_cast<const float4*>(a0 + (unsigned)e * planeBytes);
+  for (int e = 0; e < kTmaAhead; e++) q[e] = *reinterpret_cast<const float4*>(a0 + (unsigned)e * planeBytes);
 #pragma unroll 1  // one copy of the ~600-instruction body: a fully unrolled pair loop overflows the instruction cache
   for (unsigned pp = ppBegin; pp < ppStop; pp++) {
     // block 0: prologue (new = A).  Its old set B already holds tap block 1 (initial load / previous tail).
@@ -387,7 +394,7 @@ __device__ __forceinline__ void firComputePairsShort(float2 (&acc)[kTmaR], const
   }
   const unsigned char* a0 = blockAddr(ppBegin, 0);
 #pragma unroll
-  for (int e = 0; e < 6; e++) q[e] = *reinterpret_cast<const float4*>(a0 + (unsigned)e * planeBytes);
+  for (int e = 0; e < kTmaAhead; e++) q[e] = *reinterpret_cast<const float4*>(a0 + (unsigned)e * planeBytes);
 #pragma unroll 1
   for (unsigned pp = ppBegin; pp < ppStop; pp++) {
     const unsigned char* a1 = blockAddr(pp, 1);

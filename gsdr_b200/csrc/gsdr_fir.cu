@@ -187,9 +187,12 @@ struct TmaVariant {
   int threads() const { return tg * psplit; }
 };
 // X(id, TG, PSPLIT, NBUF, MINB) — ids continue after the polyphase variants
+#ifndef GSDR_EXP_MINB1
+#define GSDR_EXP_MINB1 4
+#endif
 #define GSDR_TMA_VARIANTS(X) \
   X(0, 64, 2, 2, 2)          \
-  X(1, 32, 2, 2, 4)          \
+  X(1, 32, 2, 2, GSDR_EXP_MINB1) \
   X(2, 64, 1, 2, 2)          \
   X(3, 128, 2, 2, 1)         \
   X(4, 32, 4, 2, 3)          \
