@@ -156,7 +156,8 @@ static cudaError_t launchPolyMode(int variant, PolyParams& P, size_t smem, int d
 }
 
 // Automatic choice: first variant of the preference list whose shared memory fits.
-static int choosePolyVariant(size_t D, size_t T, size_t nOut, int maxSmem, PolyGeom* geom) noexcept {
+static int choosePolyVariant(size_t D, size_t T, size_t nOut, int maxSmem, PolyGeom* geom,
+                             bool doubleBuffered = false) noexcept {
   const int forced = gForcedVariant.load(std::memory_order_relaxed);
   if (forced == -2) return -1;
   if (forced >= 0 && forced < kNumVariants) {
@@ -164,10 +165,13 @@ static int choosePolyVariant(size_t D, size_t T, size_t nOut, int maxSmem, PolyG
   }
   if (forced >= kNumVariants) return -1;  // a TMA variant was requested and did not qualify: direct kernel
   (void)nOut;
-  static const int order[] = {1, 2};
+  static const int orderSingle[] = {1, 2};
+  static const int orderDouble[] = {6, 1};  // real input, decimation 1: 64 threads, two window buffers
+  const int* order = doubleBuffered ? orderDouble : orderSingle;
   const size_t budgets[] = {(size_t)44 * 1024, (size_t)(226 * 1024) / 2, (size_t)maxSmem};
   for (size_t limit : budgets) {
-    for (int id : order) {
+    for (int k = 0; k < 2; k++) {
+      const int id = order[k];
       PolyGeom g;
       if (!polyGeometry(kVariants[id], D, T, &g)) continue;
       if (g.smemBytes <= limit && g.smemBytes <= (size_t)maxSmem) {
@@ -673,6 +677,9 @@ static int chooseRealVariant(const FirCall& c, int maxSmem, RealGeom* geom) noex
   const int forced = gForcedVariant.load(std::memory_order_relaxed);
   if (forced >= firstId) return realVariantFits(forced - firstId, c, maxSmem, geom) ? forced - firstId : -1;
   if (forced != -1) return -1;
+  // decimation 1 (one branch pair, half the FFMA2s per tile of the complex kernel) is faster on the cp.async kernel:
+  // 0.209 ms against 0.219 ms for 2^26 samples x 63 taps (tools/sweep.py --kind ff)
+  if (c.decimation == 1) return -1;
   // one branch pair (decimation 1): four filter warps + four producer warps; more pairs: smaller tiles, more CTAs
   // (tools/sweep.py --kind ff: D = 1 -> id 0 at 0.209 ms for 2^26 samples x 63 taps, D = 5 -> id 7 at 0.217 ms for 2^27)
   static const int orderOnePair[] = {0, 1, 2, 3};
@@ -810,7 +817,9 @@ cudaError_t enqueueFir(const FirCall& c, cudaStream_t stream) noexcept {
   }
   const bool polyType = (c.type == kFirFC || c.type == kFirFF);
   PolyGeom geom{};
-  const int variant = polyType ? choosePolyVariant(c.decimation, c.tapCount, c.numOutputs, info->maxSmemOptin, &geom) : -1;
+  const int variant = polyType ? choosePolyVariant(c.decimation, c.tapCount, c.numOutputs, info->maxSmemOptin, &geom,
+                                                   c.type == kFirFF && c.decimation == 1)
+                               : -1;
   if (variant < 0) {
     if (c.nco != kNcoNone) return launchDirectNco(c, stream);
     switch (c.type) {
@@ -1035,7 +1044,9 @@ GSDR_C_LINKAGE int gsdrB200DescribeKernel(int firType, size_t decimation, size_t
   }
   PolyGeom g{};
   const bool polyType = (firType == kFirFC || firType == kFirFF || firType == 4);
-  const int v = polyType ? choosePolyVariant(decimation, tapCount, numOutputs, di->maxSmemOptin, &g) : -1;
+  const int v = polyType ? choosePolyVariant(decimation, tapCount, numOutputs, di->maxSmemOptin, &g,
+                                             firType == kFirFF && decimation == 1)
+                         : -1;
   info->variant = v;
   if (v >= 0) {
     const size_t bout = (size_t)kVariants[v].R * kVariants[v].tg * (firType == kFirFF ? 2 : 1);
