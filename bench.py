@@ -161,7 +161,30 @@ def _cpu_baseline(D, T, taps, n_in_full, target_seconds=10.0):
                       f"reference's accumulation order"}
 
 
+# stdout carries exactly ONE JSON line.  Libraries loaded later write there too (NCCL prints its version line to fd 1
+# whatever NCCL_DEBUG_FILE says), so fd 1 is pointed at stderr for the life of the process and the JSON line goes to the
+# saved original.
+_REAL_STDOUT = None
+
+
+def _capture_stdout() -> None:
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def _emit(text: str) -> None:
+    sys.stdout.flush()
+    if _REAL_STDOUT is None:
+        print(text, flush=True)
+    else:
+        os.write(_REAL_STDOUT, (text + "\n").encode())
+
+
 def main() -> None:
+    _capture_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=50)
@@ -190,7 +213,7 @@ def main() -> None:
     if args.impl == "cpu":
         if rank == 0:
             cb = _cpu_baseline(D, T, taps, n_in_gpu, target_seconds=15.0)
-            print(json.dumps({"metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": 0, "steps": 1, "warmup": 0,
+            _emit(json.dumps({"metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": 0, "steps": 1, "warmup": 0,
                               "impl": "cpu", "higher_is_better": True, "dtype": "f32", "data": "synthetic",
                               "config": {"workload": wl["desc"]}, "cpu_baseline": cb,
                               "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0,
@@ -279,7 +302,7 @@ def main() -> None:
         from oracle import ref_cuda
 
         if not ref_cuda.available():
-            print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libgsdr_ref.so was not built "
+            _emit(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libgsdr_ref.so was not built "
                                                                   "(needs /root/reference at build time)"}))
             return
         if wl["nco"]:
@@ -443,7 +466,7 @@ def main() -> None:
     }
     if gather_ms is not None:
         line["gather_ms"] = gather_ms
-    print(json.dumps(line))
+    _emit(json.dumps(line))
     if dist_on:
         torch.distributed.destroy_process_group()
 
