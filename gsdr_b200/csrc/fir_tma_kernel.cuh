@@ -1000,4 +1000,175 @@ __global__ void __launch_bounds__(TG* PSPLIT + 32 * MIXW, MINB) firTmaRealKernel
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Complex taps x complex input (gsdrFirCC; replaces ref: src/fir.cu:26-71 for <cuComplex, cuComplex, cuComplex>)
+// as two real-tap filters over the same window:  out = sum x*hr + j * sum x*hi.  The branch groups split into two
+// tap planes (even groups: real parts, odd groups: imaginary parts); a group of the imaginary plane publishes its
+// partial sum already multiplied by j, (-im, re), so the fixed-order sum of the partial sums is the result.
+// Same TMA staging, layout and inner loop as firTmaKernel; the taps take twice the shared memory.
+// PSPLIT is even; the PSPLIT / 2 groups of a plane split the branch pairs.
+// ---------------------------------------------------------------------------------------------------------
+template <int TG, int PSPLIT, int DT, int NBUF, int MINB>
+__global__ void __launch_bounds__(TG* PSPLIT, MINB)
+    firTmaCcKernel(const __grid_constant__ CUtensorMap map, const TmaParams P) {
+  static_assert(NBUF == 1 || NBUF == 2, "one or two window buffers");
+  static_assert(PSPLIT >= 2 && PSPLIT % 2 == 0, "two tap planes");
+  constexpr unsigned NT = TG * PSPLIT;
+  constexpr unsigned BOUT = kTmaR * TG;
+  constexpr unsigned NSUB = PSPLIT / 2;
+  extern __shared__ __align__(16) unsigned char smemRaw[];
+  __shared__ __align__(8) unsigned long long fullBar[2];
+  const unsigned D = DT ? (unsigned)DT : P.D;
+  const unsigned rowBytes = 8u * D;
+  const unsigned segBytes = DT ? tmaSegBytes(DT ? DT : 2) : P.segBytes;
+  const unsigned numSegs = rowBytes / segBytes;
+  const unsigned planeBytes = DT ? tmaPlaneRows(TG, kTmaJpadCap, DT ? DT : 2) * segBytes : P.planeBytes;
+  const unsigned bufBytes = numSegs * 8u * planeBytes;
+  unsigned char* bufBase = smemRaw + ((1024u - (smemU32(smemRaw) & 1023u)) & 1023u);
+  float4* scratch = reinterpret_cast<float4*>(bufBase + NBUF * bufBytes);
+  float* hs = reinterpret_cast<float*>(scratch + 2u * (PSPLIT - 1) * (kTmaR / 2) * TG);  // 2 x ([D/2][Jpad][2] + 32)
+  const unsigned tapPlaneFloats = D * P.Jpad + 32u;
+
+  const unsigned tid = threadIdx.x;
+  const unsigned grp = tid / TG;
+  const unsigned t = tid - grp * TG;
+  const unsigned plane = grp & 1u, sub = grp >> 1;
+  const unsigned numPairs = D >> 1;
+  const unsigned ppBegin = (sub * numPairs) / NSUB;
+  const unsigned ppEnd = ((sub + 1) * numPairs) / NSUB;
+  const unsigned rowsStaged = BOUT + P.Jpad;
+
+  if (tid == 0) {
+    mbarInit(&fullBar[0], 1);
+    mbarInit(&fullBar[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  unsigned chan = blockIdx.x / P.tilesPerChannel;
+  unsigned tile = blockIdx.x - chan * P.tilesPerChannel;
+  auto advance = [&](unsigned& c, unsigned& tl) {
+    c += P.strideChan;
+    tl += P.strideTile;
+    if (tl >= P.tilesPerChannel) {
+      tl -= P.tilesPerChannel;
+      c += 1;
+    }
+  };
+  auto tileIsFast = [&](unsigned tl) -> bool { return tl * BOUT + rowsStaged <= P.tmaRows; };
+  auto issueTile = [&](unsigned c, unsigned tl, unsigned b) {
+    unsigned char* buf = bufBase + b * bufBytes;
+    if (tileIsFast(tl)) {
+      if (tid == 0) {
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        mbarExpectTx(&fullBar[b], bufBytes);
+        for (unsigned sg = 0; sg < numSegs; sg++) {
+          tmaLoad4(buf + sg * 8u * planeBytes, &map, &fullBar[b], (int)(sg * (segBytes / 4u)), (int)(tl * (BOUT / 8)), 0,
+                   (int)c);
+        }
+      }
+    } else {
+      tmaStageSlow<NT, DT>(buf, P.x + (size_t)c * P.xStride, (unsigned long long)tl * BOUT * D, rowsStaged, planeBytes, P);
+    }
+  };
+
+  unsigned phaseBits = 0;
+  if (NBUF == 2) {
+    if (chan < P.numChannels) issueTile(chan, tile, 0);
+    asm volatile("cp.async.commit_group;\n" ::: "memory");
+  }
+  unsigned tapsChan = 0xffffffffu;
+
+  for (unsigned it = 0; chan < P.numChannels; it++) {
+    const unsigned b = (NBUF == 2) ? (it & 1u) : 0u;
+    const unsigned char* buf = bufBase + b * bufBytes;
+    const unsigned long long o0 = (unsigned long long)tile * BOUT;
+    unsigned nextChan = chan, nextTile = tile;
+    advance(nextChan, nextTile);
+    if (NBUF == 2) {
+      if (nextChan < P.numChannels) issueTile(nextChan, nextTile, b ^ 1u);
+    } else {
+      issueTile(chan, tile, 0);
+    }
+    asm volatile("cp.async.commit_group;\n" ::: "memory");
+
+    // taps: plane 0 = real parts, plane 1 = imaginary parts, each laid out like firTmaKernel's hs2
+    const bool tapsReloaded = chan != tapsChan && (tapsChan == 0xffffffffu || P.hStride != 0);
+    if (tapsReloaded) {
+      const float* h = P.h + 2u * (size_t)chan * P.hStride;  // interleaved (re, im)
+      const unsigned nh = D * P.Jpad;
+      for (unsigned i = tid; i < 2u * tapPlaneFloats; i += NT) {
+        const unsigned pl = i >= tapPlaneFloats ? 1u : 0u;
+        const unsigned k = i - pl * tapPlaneFloats;
+        const unsigned pp = k / (2u * P.Jpad);
+        const unsigned rem = k - pp * 2u * P.Jpad;
+        const unsigned ti = (rem >> 1) * D + 2u * pp + (rem & 1u);
+        hs[i] = (k < nh && ti < P.T) ? __ldg(h + 2u * ti + pl) : 0.0f;
+      }
+    }
+    tapsChan = chan;
+
+    const bool fast = tileIsFast(tile);
+    if (fast) {
+      mbarWait(&fullBar[b], (phaseBits >> b) & 1u);
+      phaseBits ^= 1u << b;
+    }
+    if (!fast || tapsReloaded) {
+      if (NBUF == 2) {
+        asm volatile("cp.async.wait_group 1;\n" ::: "memory");
+      } else {
+        asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+      }
+      __syncthreads();
+    }
+
+    float2 acc[kTmaR];
+#pragma unroll
+    for (int r = 0; r < kTmaR; r++) acc[r] = make_float2(0.0f, 0.0f);
+    if (ppBegin < ppEnd) {
+      firComputePairs<DT>(acc, buf, hs + plane * tapPlaneFloats, t, ppBegin, ppEnd, P.Jpad, planeBytes, P);
+    }
+    if (grp > 0) {
+      float4* red = scratch + (size_t)(it & 1u) * (PSPLIT - 1) * (kTmaR / 2) * TG;
+#pragma unroll
+      for (int k = 0; k < kTmaR / 2; k++) {
+        red[((grp - 1) * (kTmaR / 2) + k) * TG + t] =
+            plane ? make_float4(-acc[2 * k].y, acc[2 * k].x, -acc[2 * k + 1].y, acc[2 * k + 1].x)
+                  : make_float4(acc[2 * k].x, acc[2 * k].y, acc[2 * k + 1].x, acc[2 * k + 1].y);
+      }
+    }
+    __syncthreads();
+    if (grp == 0) {
+      const float4* red = scratch + (size_t)(it & 1u) * (PSPLIT - 1) * (kTmaR / 2) * TG;
+#pragma unroll
+      for (int g = 1; g < PSPLIT; g++) {
+#pragma unroll
+        for (int k = 0; k < kTmaR / 2; k++) {
+          const float4 v = red[((g - 1) * (kTmaR / 2) + k) * TG + t];
+          acc[2 * k].x += v.x;
+          acc[2 * k].y += v.y;
+          acc[2 * k + 1].x += v.z;
+          acc[2 * k + 1].y += v.w;
+        }
+      }
+      const unsigned long long ob = o0 + (unsigned long long)t * kTmaR;
+      float2* y = P.y + (size_t)chan * P.yStride;
+      if (P.y16 && ob + kTmaR <= P.nOut) {
+#pragma unroll
+        for (int r = 0; r < kTmaR; r += 2) {
+          *reinterpret_cast<float4*>(y + ob + r) = make_float4(acc[r].x, acc[r].y, acc[r + 1].x, acc[r + 1].y);
+        }
+      } else {
+#pragma unroll
+        for (int r = 0; r < kTmaR; r++) {
+          if (ob + r < P.nOut) y[ob + r] = acc[r];
+        }
+      }
+    }
+    chan = nextChan;
+    tile = nextTile;
+  }
+  asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+}
+
 }  // namespace gsdr_b200

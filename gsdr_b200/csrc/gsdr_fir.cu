@@ -260,6 +260,21 @@ static constexpr RealVariant kRealVariants[] = {
 };
 static constexpr int kNumRealVariants = (int)(sizeof(kRealVariants) / sizeof(kRealVariants[0]));
 
+// Complex-tap kernel (firTmaCcKernel): X(id, TG, PSPLIT, NBUF, MINB), PSPLIT even (two tap planes); ids continue
+// after the real-input variants
+#define GSDR_CC_VARIANTS(X) \
+  X(0, 32, 2, 2, 4)         \
+  X(1, 32, 4, 2, 3)         \
+  X(2, 64, 2, 2, 2)         \
+  X(3, 32, 4, 1, 2)
+
+static constexpr TmaVariant kCcVariants[] = {
+#define X(id, tg, ps, nb, mb) {tg, ps, nb, mb},
+    GSDR_CC_VARIANTS(X)
+#undef X
+};
+static constexpr int kNumCcVariants = (int)(sizeof(kCcVariants) / sizeof(kCcVariants[0]));
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -508,11 +523,105 @@ static int chooseTmaVariant(const FirCall& c, int maxSmem, TmaGeom* geom) noexce
   return -1;
 }
 
-static cudaError_t launchTma(const FirCall& c, int variant, const TmaGeom& geom, int dev, int smCount,
+// ---- complex taps (gsdrFirCC): two tap planes on the same windows ----
+static bool ccGeometry(const TmaVariant& v, size_t D, size_t T, TmaGeom* g) noexcept {
+  TmaVariant half = v;
+  half.psplit = v.psplit / 2;  // groups per tap plane: they split the branch pairs
+  if (!tmaGeometry(half, D, T, g)) return false;
+  if (g->staticD && D != 8) {
+    // only D = 8 has a compile-time-geometry instantiation of this kernel: recompute the plane pitch for run time
+    g->staticD = false;
+    const size_t G = tmaSegBytes((unsigned)D);
+    const size_t mhp = tmaPlaneRows((unsigned)v.tg, g->Jpad, (unsigned)D);
+    if (mhp > 256) return false;
+    g->mhp = (unsigned)mhp;
+    g->planeBytes = (unsigned)(mhp * G);
+  }
+  g->smemBytes = 1024 + (size_t)v.nbuf * (8 * D / tmaSegBytes((unsigned)D)) * 8 * (size_t)g->planeBytes +
+                 2 * (size_t)(v.psplit - 1) * v.tg * 64 + 2 * (D * g->Jpad + 32) * 4;
+  return true;
+}
+
+template <int TG, int PSPLIT, int DT, int NBUF, int MINB>
+static cudaError_t launchCcT(const CUtensorMap& map, TmaParams& P, size_t smem, int dev, int smCount,
                              cudaStream_t stream) noexcept {
+  static std::atomic<size_t> configured[64];
+  auto kernel = firTmaCcKernel<TG, PSPLIT, DT, NBUF, MINB>;
+  if (smem > configured[dev & 63].load(std::memory_order_acquire)) {
+    cudaError_t st = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (st != cudaSuccess) return report(st, "cudaFuncSetAttribute(MaxDynamicSharedMemorySize)");
+    configured[dev & 63].store(smem, std::memory_order_release);
+  }
+  int perSm = 0;
+  cudaError_t st = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, kernel, TG * PSPLIT, smem);
+  if (st != cudaSuccess) return report(st, "cudaOccupancyMaxActiveBlocksPerMultiprocessor");
+  if (perSm < 1) return cudaErrorInvalidConfiguration;
+  {
+    const int warpsPerCta = (TG * PSPLIT) / 32;
+    int balanced = perSm;
+    while (balanced > 1 && (balanced * warpsPerCta) % 4 != 0) balanced--;
+    if ((balanced * warpsPerCta) % 4 == 0) perSm = balanced;
+  }
+  const unsigned long long resident = (unsigned long long)perSm * (unsigned)smCount;
+  const unsigned grid = (unsigned)(P.totalTiles < resident ? P.totalTiles : resident);
+  P.strideChan = grid / P.tilesPerChannel;
+  P.strideTile = grid % P.tilesPerChannel;
+  void* args[] = {(void*)&map, (void*)&P};
+  return cudaLaunchKernel((const void*)kernel, dim3(grid), dim3(TG * PSPLIT), args, smem, stream);
+}
+
+template <int DT>
+static cudaError_t launchCcD(int variant, const CUtensorMap& map, TmaParams& P, size_t smem, int dev, int smCount,
+                             cudaStream_t stream) noexcept {
+  switch (variant) {
+#define X(id, tg, ps, nb, mb) \
+  case id: return launchCcT<tg, ps, DT, nb, mb>(map, P, smem, dev, smCount, stream);
+    GSDR_CC_VARIANTS(X)
+#undef X
+    default: return cudaErrorInvalidValue;
+  }
+}
+
+static int firstCcVariantId() noexcept { return kNumVariants + kNumTmaVariants + kNumSpecVariants + kNumRealVariants; }
+
+// Returns the complex-tap variant for this call, or -1 when the call does not qualify.
+static int chooseCcVariant(const FirCall& c, int maxSmem, TmaGeom* geom) noexcept {
+  if (c.type != kFirCC || c.nco != kNcoNone) return -1;
+  if (!tmaSupportedDecimation(c.decimation) || !encodeTiled()) return -1;
+  if ((uintptr_t)c.input % 16 != 0) return -1;
+  if (c.numChannels > 1 && (c.inputStride % 2) != 0) return -1;
+  if (c.numChannels > 0x7fffffffull) return -1;
+  auto fits = [&](int id, TmaGeom* g) {
+    return id >= 0 && id < kNumCcVariants && ccGeometry(kCcVariants[id], c.decimation, c.tapCount, g) &&
+           g->smemBytes <= (size_t)maxSmem;
+  };
+  const int forced = gForcedVariant.load(std::memory_order_relaxed);
+  if (forced >= firstCcVariantId()) return fits(forced - firstCcVariantId(), geom) ? forced - firstCcVariantId() : -1;
+  if (forced != -1) return -1;
+  static const int orderNarrow[] = {0, 1, 3, 2};
+  static const int orderWide[] = {1, 3, 0, 2};
+  const int* order = c.decimation > 16 ? orderWide : orderNarrow;
+  for (int k = 0; k < 4; k++) {
+    TmaGeom g;
+    if (fits(order[k], &g)) {
+      *geom = g;
+      return order[k];
+    }
+  }
+  return -1;
+}
+
+// variant: a TMA / fused-NCO variant id, or (ccVariant >= 0) a complex-tap variant
+static cudaError_t launchTma(const FirCall& c, int variant, const TmaGeom& geom, int dev, int smCount,
+                             cudaStream_t stream, int ccVariant = -1) noexcept {
   TmaVariant v;
   int mixw = 0;
-  if (!tmaVariantShape(variant, &v, &mixw)) return cudaErrorInvalidValue;
+  if (ccVariant >= 0) {
+    if (ccVariant >= kNumCcVariants) return cudaErrorInvalidValue;
+    v = kCcVariants[ccVariant];
+  } else if (!tmaVariantShape(variant, &v, &mixw)) {
+    return cudaErrorInvalidValue;
+  }
   const size_t bout = (size_t)kTmaR * v.tg;
   const unsigned long long tiles = (c.numOutputs + bout - 1) / bout;
   const unsigned long long total = tiles * c.numChannels;
@@ -570,6 +679,10 @@ static cudaError_t launchTma(const FirCall& c, int variant, const TmaGeom& geom,
       return cudaErrorInvalidValue;
     }
     if (tmaRows < 8) P.tmaRows = 0;
+  }
+  if (ccVariant >= 0) {
+    if (geom.staticD && D == 8) return launchCcD<8>(ccVariant, map, P, geom.smemBytes, dev, smCount, stream);
+    return launchCcD<0>(ccVariant, map, P, geom.smemBytes, dev, smCount, stream);
   }
   if (mixw > 0) {
     return launchSpec(variant - kNumTmaVariants, geom.staticD, map, P, geom.smemBytes, dev, smCount, stream);
@@ -814,6 +927,8 @@ cudaError_t enqueueFir(const FirCall& c, cudaStream_t stream) noexcept {
     RealGeom rg{};
     const int rv = chooseRealVariant(c, info->maxSmemOptin, &rg);
     if (rv >= 0) return launchReal(c, rv, rg, dev, info->smCount, stream);
+    const int cv = chooseCcVariant(c, info->maxSmemOptin, &tg);
+    if (cv >= 0) return launchTma(c, -1, tg, dev, info->smCount, stream, cv);
   }
   const bool polyType = (c.type == kFirFC || c.type == kFirFF);
   PolyGeom geom{};
@@ -968,13 +1083,13 @@ GSDR_C_LINKAGE uint64_t gsdrNcoPhaseStep(float frequencyShift, float sampleRate)
 // ---- tuning / introspection hooks of <gsdr/b200.h> -------------------------------------------------------
 
 GSDR_C_LINKAGE int gsdrB200SetKernelVariant(int variant) GSDR_NO_EXCEPT {
-  if (variant < -2 || variant >= kNumVariants + kNumTmaVariants + kNumSpecVariants + kNumRealVariants) return -1;
+  if (variant < -2 || variant >= firstCcVariantId() + kNumCcVariants) return -1;
   gForcedVariant.store(variant, std::memory_order_relaxed);
   return 0;
 }
 
 GSDR_C_LINKAGE int gsdrB200NumKernelVariants(void) GSDR_NO_EXCEPT {
-  return kNumVariants + kNumTmaVariants + kNumSpecVariants + kNumRealVariants;
+  return firstCcVariantId() + kNumCcVariants;
 }
 GSDR_C_LINKAGE int gsdrB200NumPolyphaseVariants(void) GSDR_NO_EXCEPT { return kNumVariants; }
 
@@ -1016,6 +1131,28 @@ GSDR_C_LINKAGE int gsdrB200DescribeKernel(int firType, size_t decimation, size_t
       info->windowBuffers = vs.nbuf;
       info->outputsPerBlock = bout;
       info->sharedBytesPerBlock = tg.smemBytes;
+      info->numBlocks = (numOutputs + bout - 1) / bout;
+      return 0;
+    }
+  }
+  if (firType == kFirCC) {
+    FirCall probe;
+    probe.type = kFirCC;
+    probe.decimation = decimation;
+    probe.tapCount = tapCount;
+    probe.numOutputs = numOutputs;
+    TmaGeom cg{};
+    const int cv = chooseCcVariant(probe, di->maxSmemOptin, &cg);
+    if (cv >= 0) {
+      const TmaVariant& vs = kCcVariants[cv];
+      const size_t bout = (size_t)kTmaR * vs.tg;
+      info->variant = firstCcVariantId() + cv;
+      info->outputsPerThread = kTmaR;
+      info->threadsPerBlock = vs.threads();
+      info->phaseGroups = vs.psplit;
+      info->windowBuffers = vs.nbuf;
+      info->outputsPerBlock = bout;
+      info->sharedBytesPerBlock = cg.smemBytes;
       info->numBlocks = (numOutputs + bout - 1) / bout;
       return 0;
     }

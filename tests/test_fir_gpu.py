@@ -90,8 +90,8 @@ def test_polyphase_against_oracle(kind, D, T, n_in, cuda_device):
         assert np.abs(y.astype(truth.dtype) - truth).max() <= _tol(taps, x)
 
 
-# polyphase (cp.async) | TMA-fed | warp-specialised fused NCO | real-input variants
-N_POLY, N_TMA, N_SPEC, N_ALL = 12, 24, 30, 40
+# polyphase (cp.async) | TMA-fed | warp-specialised fused NCO | real-input | complex-tap variants
+N_POLY, N_TMA, N_SPEC, N_REAL, N_ALL = 12, 24, 30, 40, 44
 
 
 @pytest.mark.parametrize("variant", [-2] + list(range(N_ALL)))
@@ -119,7 +119,7 @@ def test_every_kernel_variant(kind, variant, cuda_device):
         assert np.abs(y - want).max() <= _tol(taps, x)
 
 
-@pytest.mark.parametrize("variant", list(range(N_SPEC, N_ALL)))
+@pytest.mark.parametrize("variant", list(range(N_SPEC, N_REAL)))
 @pytest.mark.parametrize("D,T,n_out", [(1, 63, 70_001), (1, 7, 5000), (2, 100, 40_000), (3, 17, 33_333), (4, 127, 30_001),
                                        (5, 63, 50_001), (5, 200, 20_000), (7, 29, 9_999), (8, 255, 20_000),
                                        (16, 1023, 9_000), (64, 300, 2_001)])
@@ -147,6 +147,35 @@ def test_real_input_kernel(variant, D, T, n_out, cuda_device):
     g.gsdrFirFF(D, dt, T, dx, dy2[1:], n_out, 0, None)
     torch.cuda.synchronize()
     assert dy2[1:].cpu().numpy().tobytes() == y[:n_out].tobytes()
+
+
+@pytest.mark.parametrize("variant", [-1] + list(range(N_REAL, N_ALL)))
+@pytest.mark.parametrize("D,T,n_out", [(8, 255, 40_001), (2, 33, 10_000), (4, 127, 30_000), (10, 100, 9_999),
+                                       (16, 500, 7_000), (32, 1023, 5_000), (6, 7, 3_000)])
+def test_complex_tap_kernel(variant, D, T, n_out, cuda_device):
+    """gsdrFirCC as two real-tap filters on the same windows (real and imaginary tap planes, the second published
+    multiplied by j).  Accumulation order differs from the reference's: tolerance, not bits."""
+    taps = synth.random_taps(T, 19 + D, complex_taps=True)
+    x = synth.tone_plus_noise(0, (n_out - 1) * D + T, seed=110 + D)
+    g.set_kernel_variant(variant)
+    info = g.describe_kernel(2, D, T, n_out)
+    if variant >= 0 and info.variant == -1:
+        pytest.skip("variant does not fit this shape")
+    assert info.variant >= N_REAL and (variant < 0 or info.variant == variant)
+    y = _run("cc", D, taps, x, n_out, cuda_device)
+    want = oracle.fir("cc", D, taps, x, n_out, threads=8)
+    assert np.abs(y - want).max() <= _tol(taps, x)
+
+
+def test_complex_taps_batched_and_unaligned(cuda_device):
+    D, T, n_out = 8, 255, 6000
+    taps = synth.random_taps(T, 23, complex_taps=True)
+    x = synth.tone_plus_noise(0, (n_out - 1) * D + T + 1, seed=120)
+    dt, dx = torch.from_numpy(taps).to(cuda_device), torch.from_numpy(x).to(cuda_device)
+    dy = torch.zeros(n_out, dtype=torch.complex64, device=cuda_device)
+    g.gsdrFirCC(D, dt, T, dx[1:], dy, n_out, 0, None)  # 8-byte aligned input: direct kernel, the reference's bits
+    torch.cuda.synchronize()
+    assert dy.cpu().numpy().tobytes() == oracle.fir("cc", D, taps, x[1:], n_out).tobytes()
 
 
 def test_real_input_batched_and_unaligned(cuda_device):

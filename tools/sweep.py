@@ -51,16 +51,17 @@ def main():
     real = args.kind == "ff"
     n_out = g.fir_num_outputs(n_in, T, D)
     x = synth.tone_plus_noise(0, n_in, seed=1, device=dev, real=real)
-    taps = torch.from_numpy(synth.lowpass_taps(T, D)).to(dev)
+    cc = args.kind == "cc"
+    taps = torch.from_numpy(synth.random_taps(T, 3, complex_taps=True) if cc else synth.lowpass_taps(T, D)).to(dev)
     y = torch.zeros(n_out, dtype=torch.float32 if real else torch.complex64, device=dev)
     stream = torch.cuda.Stream()
-    fn = g.gsdrFirFF if real else g.gsdrFirFC
+    fn = g.gsdrFirFF if real else (g.gsdrFirCC if cc else g.gsdrFirFC)
     if args.nco:
         def fn(D_, taps_, T_, x_, y_, n_, dev_, stream_):  # noqa: E306
             g.gsdrAdjustFrequencyFirFC(2.4e6, 29520.0, 12345, D_, taps_, T_, x_, y_, n_, dev_, stream_)
     esz = 4 if real else 8
     bytes_alg = esz * n_in + esz * n_out + 4 * T
-    flops = (2.0 if real else 4.0) * T * n_out
+    flops = (2.0 if real else (8.0 if cc else 4.0)) * T * n_out
     if args.peaks:
         lib = ctypes.CDLL(str(ROOT / "tools" / "libubench_fp32.so"))
         lib.ubenchFp32Tflops.restype = ctypes.c_double
@@ -77,7 +78,7 @@ def main():
     ref = None
     for v in list(range(g.num_kernel_variants())) + [-2]:
         g.set_kernel_variant(v)
-        info = g.describe_kernel(1 if real else (4 if args.nco else 0), D, T, n_out)
+        info = g.describe_kernel(1 if real else (2 if cc else (4 if args.nco else 0)), D, T, n_out)
         if v >= 0 and info.variant != v:
             print(json.dumps({"variant": v, "skipped": "does not fit"}), flush=True)
             continue
