@@ -27,6 +27,9 @@
  *    launch errors are reported (the reference never calls cudaGetLastError).
  *  - Floating point: FP32 FMA accumulation in a different order than the reference's single ascending chain;
  *    max |err| <= 1e-5 * sum|taps| * max|input| against it.
+ *  - NEW: the staged kernels pad the tap set with zeros up to a multiple of 8 or 16 taps per polyphase branch, so an
+ *    Inf or NaN input sample can reach outputs up to 16 * decimation samples earlier than the reference's window
+ *    would (0 * Inf = NaN); finite inputs are unaffected.
  */
 #ifndef GSDR_B200_INCLUDE_GSDR_FIR_H_
 #define GSDR_B200_INCLUDE_GSDR_FIR_H_
