@@ -501,11 +501,12 @@ static int chooseTmaVariant(const FirCall& c, int maxSmem, TmaGeom* geom) noexce
   // 2 / 4 groups, 4 = (32 x 4, double buffered), 11 = (32 x 8, single buffered)
   static const int orderEvenPairs[] = {1, 8, 5, 0};   // D = 8, 16: the branch pairs split evenly over 2 groups
   static const int orderOddPairs[] = {8, 1, 5, 0};    // D = 2, 4, 6, 10, 14: one group keeps all pairs
-  static const int orderWide[] = {4, 10, 11, 1};
+  static const int orderWide[] = {10, 4, 11, 1};       // D >= 16 (1023 taps, D = 32, 2^27: 0.391 / 0.401 ms; 511 taps,
+                                                       // D = 16, 2^26: 0.205 / 0.206 ms, id 1: 0.219 ms)
   static const int orderNarrowNcoEven[] = {6, 9, 5, 1};  // 6 = (64 x 2, single buffer), 9 = (64 x 1, single buffer)
   static const int orderNarrowNcoOdd[] = {9, 6, 5, 1};
   static const int orderWideNco[] = {10, 11, 4, 1};
-  const bool wide = c.decimation > 16;
+  const bool wide = c.decimation >= 16;
   const bool nco = c.nco != kNcoNone;
   const bool evenPairs = ((c.decimation / 2) % 2 == 0) && c.decimation >= 8;
   const int* order = wide ? (nco ? orderWideNco : orderWide)
