@@ -15,7 +15,8 @@ from pathlib import Path
 ROOT = Path(__file__).resolve().parent.parent
 CSRC = ROOT / "gsdr_b200" / "csrc"
 LIB = CSRC / "libgsdr_b200.so"
-SOURCES = [CSRC / "gsdr_fir.cu", CSRC / "gsdr_host.cu", CSRC / "gsdr_demod.cu", CSRC / "gsdr_stream.cu"]
+SOURCES = [CSRC / "gsdr_fir.cu", CSRC / "gsdr_host.cu", CSRC / "gsdr_demod.cu", CSRC / "gsdr_stream.cu",
+           *sorted(CSRC.glob("fir_inst_*.cu"))]  # fir_inst_*: kernel instantiations, one unit per compile-time decimation
 HEADERS = sorted(CSRC.glob("*.cuh")) + sorted(CSRC.glob("*.h")) + sorted((ROOT / "include" / "gsdr").glob("*.h"))
 
 NVCC_FLAGS = [
@@ -48,15 +49,38 @@ def _stale(target: Path, deps) -> bool:
 
 
 def build_library(force: bool = False, verbose: bool = False) -> Path:
+    """Every translation unit is compiled to an object by its own nvcc process (in parallel), then linked."""
     if not force and not _stale(LIB, SOURCES + HEADERS + [Path(__file__)]):
         return LIB
-    cmd = [_nvcc(), *NVCC_FLAGS, "-shared", "-I", str(ROOT / "include"), "-I", str(CSRC),
-           "-o", str(LIB), *map(str, SOURCES)]
-    res = subprocess.run(cmd, capture_output=True, text=True)
-    log = res.stdout + res.stderr
-    (CSRC / "build.log").write_text(" ".join(cmd) + "\n" + log)
-    if res.returncode != 0:
-        sys.stderr.write(log)
+    from concurrent.futures import ThreadPoolExecutor
+
+    objdir = CSRC / "build"
+    objdir.mkdir(exist_ok=True)
+    nvcc = _nvcc()
+
+    def compile_one(src: Path):
+        obj = objdir / (src.stem + ".o")
+        cmd = [nvcc, *NVCC_FLAGS, "-c", "-I", str(ROOT / "include"), "-I", str(CSRC), "-o", str(obj), str(src)]
+        res = subprocess.run(cmd, capture_output=True, text=True)
+        return obj, cmd, res
+
+    # biggest units first so that they do not end up alone at the tail
+    order = sorted(SOURCES, key=lambda p: (0 if p.name.startswith("fir_inst_") or p.name == "gsdr_fir.cu" else 1, p.name))
+    with ThreadPoolExecutor(max_workers=max(1, min(len(order), os.cpu_count() or 1))) as pool:
+        results = list(pool.map(compile_one, order))
+    log = ""
+    failed = False
+    for obj, cmd, res in results:
+        log += " ".join(cmd) + "\n" + res.stdout + res.stderr
+        failed = failed or res.returncode != 0
+    if not failed:
+        cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", str(LIB), *[str(o) for o, _, _ in results]]
+        res = subprocess.run(cmd, capture_output=True, text=True)
+        log += " ".join(cmd) + "\n" + res.stdout + res.stderr
+        failed = res.returncode != 0
+    (CSRC / "build.log").write_text(log)
+    if failed:
+        sys.stderr.write(log[-8000:])
         raise RuntimeError("nvcc failed building libgsdr_b200.so")
     if verbose:
         print(log)

@@ -11,16 +11,14 @@
 #include <cstdlib>
 #include <mutex>
 
-#include "fir_kernels.cuh"
-#include "fir_tma_kernel.cuh"
-#include "launch.h"
+#include "fir_launch.cuh"
 
 namespace gsdr_b200 {
 
 // ---------------------------------------------------------------------------------------------------------
 // device scope + error reporting (one stderr line on failure, ref: include/gsdr/cuda_util.h:59-82)
 // ---------------------------------------------------------------------------------------------------------
-static cudaError_t report(cudaError_t st, const char* what) noexcept {
+cudaError_t report(cudaError_t st, const char* what) noexcept {
   if (st != cudaSuccess) {
     std::fprintf(stderr, "gsdr-b200: error %d - %s - %s\n", (int)st, cudaGetErrorName(st), what);
     (void)cudaGetLastError();  // the error is returned to the caller; do not leave it in the runtime's last-error slot
@@ -186,95 +184,6 @@ static int choosePolyVariant(size_t D, size_t T, size_t nOut, int maxSmem, PolyG
 // ---------------------------------------------------------------------------------------------------------
 // TMA-fed fast path (fir_tma_kernel.cuh)
 // ---------------------------------------------------------------------------------------------------------
-struct TmaVariant {
-  int tg, psplit, nbuf, minBlocks;
-  int threads() const { return tg * psplit; }
-};
-// X(id, TG, PSPLIT, NBUF, MINB) — ids continue after the polyphase variants
-#ifndef GSDR_EXP_MINB1
-#define GSDR_EXP_MINB1 4
-#endif
-#define GSDR_TMA_VARIANTS(X) \
-  X(0, 64, 2, 2, 2)          \
-  X(1, 32, 2, 2, GSDR_EXP_MINB1) \
-  X(2, 64, 1, 2, 2)          \
-  X(3, 128, 2, 2, 1)         \
-  X(4, 32, 4, 2, 3)          \
-  X(5, 32, 2, 1, 6)          \
-  X(6, 64, 2, 1, 4)          \
-  X(7, 32, 1, 1, 8)          \
-  X(8, 32, 1, 2, 5)          \
-  X(9, 64, 1, 1, 4)          \
-  X(10, 32, 4, 1, 2)         \
-  X(11, 32, 8, 1, 1)
-
-static constexpr TmaVariant kTmaVariants[] = {
-#define X(id, tg, ps, nb, mb) {tg, ps, nb, mb},
-    GSDR_TMA_VARIANTS(X)
-#undef X
-};
-static constexpr int kNumTmaVariants = (int)(sizeof(kTmaVariants) / sizeof(kTmaVariants[0]));
-
-// Warp-specialised fused-NCO kernel: X(id, TG, PSPLIT, MIXW, MINB); ids continue after the TMA variants
-#define GSDR_SPEC_VARIANTS(X) \
-  X(0, 32, 2, 2, 4)           \
-  X(1, 32, 4, 4, 1)           \
-  X(2, 64, 2, 4, 2)           \
-  X(3, 32, 1, 1, 4)           \
-  X(4, 32, 2, 1, 4)           \
-  X(5, 32, 4, 2, 2)
-
-struct SpecVariant {
-  int tg, psplit, mixw, minBlocks;
-  int threads() const { return tg * psplit + 32 * mixw; }
-};
-static constexpr SpecVariant kSpecVariants[] = {
-#define X(id, tg, ps, mw, mb) {tg, ps, mw, mb},
-    GSDR_SPEC_VARIANTS(X)
-#undef X
-};
-static constexpr int kNumSpecVariants = (int)(sizeof(kSpecVariants) / sizeof(kSpecVariants[0]));
-
-// Real-input kernel (firTmaRealKernel): X(id, TG, PSPLIT, MIXW, NWIN, NRAW, MINB); ids continue after the fused-NCO
-// variants.  NRAW - 1 bulk copies are in flight per CTA: low-rate (HBM-bound) shapes want 3 or 4.
-#define GSDR_REAL_VARIANTS(X) \
-  X(0, 128, 1, 4, 2, 2, 2)    \
-  X(1, 64, 1, 2, 2, 2, 4)     \
-  X(2, 32, 1, 1, 2, 3, 8)     \
-  X(3, 32, 1, 1, 1, 3, 8)     \
-  X(4, 64, 2, 4, 2, 3, 2)     \
-  X(5, 64, 1, 2, 1, 3, 4)     \
-  X(6, 32, 1, 1, 1, 4, 8)     \
-  X(7, 128, 1, 4, 1, 3, 2)    \
-  X(8, 64, 1, 2, 1, 4, 4)     \
-  X(9, 128, 1, 4, 1, 4, 2)
-
-struct RealVariant {
-  int tg, psplit, mixw, nwin, nraw, minBlocks;
-  int threads() const { return tg * psplit + 32 * mixw; }
-};
-static constexpr RealVariant kRealVariants[] = {
-#define X(id, tg, ps, mw, nw, nr, mb) {tg, ps, mw, nw, nr, mb},
-    GSDR_REAL_VARIANTS(X)
-#undef X
-};
-static constexpr int kNumRealVariants = (int)(sizeof(kRealVariants) / sizeof(kRealVariants[0]));
-
-// Complex-tap kernel (firTmaCcKernel): X(id, TG, PSPLIT, NBUF, MINB), PSPLIT even (two tap planes); ids continue
-// after the real-input variants
-#define GSDR_CC_VARIANTS(X) \
-  X(0, 32, 2, 2, 4)         \
-  X(1, 32, 4, 2, 3)         \
-  X(2, 64, 2, 2, 2)         \
-  X(3, 32, 4, 1, 2)
-
-static constexpr TmaVariant kCcVariants[] = {
-#define X(id, tg, ps, nb, mb) {tg, ps, nb, mb},
-    GSDR_CC_VARIANTS(X)
-#undef X
-};
-static constexpr int kNumCcVariants = (int)(sizeof(kCcVariants) / sizeof(kCcVariants[0]));
-
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -335,100 +244,17 @@ static bool tmaGeometry(const TmaVariant& v, size_t D, size_t T, TmaGeom* g) noe
   return true;
 }
 
-template <int MODE, int TG, int PSPLIT, int DT, int NBUF, int MINB>
-static cudaError_t launchTmaT(const CUtensorMap& map, TmaParams& P, size_t smem, int dev, int smCount,
-                              cudaStream_t stream) noexcept {
-  static std::atomic<size_t> configured[64];
-  auto kernel = firTmaKernel<MODE, TG, PSPLIT, DT, NBUF, MINB>;
-  if (smem > configured[dev & 63].load(std::memory_order_acquire)) {
-    cudaError_t st = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (st != cudaSuccess) return report(st, "cudaFuncSetAttribute(MaxDynamicSharedMemorySize)");
-    configured[dev & 63].store(smem, std::memory_order_release);
-  }
-  int perSm = 0;
-  cudaError_t st = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, kernel, TG * PSPLIT, smem);
-  if (st != cudaSuccess) return report(st, "cudaOccupancyMaxActiveBlocksPerMultiprocessor");
-  if (perSm < 1) return cudaErrorInvalidConfiguration;
-  // Warps are pinned to one of the SM's four sub-partitions; with a static tile assignment the kernel runs at the
-  // pace of the fullest one, so keep the resident warp count per SM a multiple of 4 (profiles/r01_notes.md).
-  {
-    const int warpsPerCta = (TG * PSPLIT) / 32;
-    int balanced = perSm;
-    while (balanced > 1 && (balanced * warpsPerCta) % 4 != 0) balanced--;
-    if ((balanced * warpsPerCta) % 4 == 0) perSm = balanced;
-  }
-  const unsigned long long resident = (unsigned long long)perSm * (unsigned)smCount;
-  const unsigned grid = (unsigned)(P.totalTiles < resident ? P.totalTiles : resident);
-  P.strideChan = grid / P.tilesPerChannel;
-  P.strideTile = grid % P.tilesPerChannel;
-  void* args[] = {(void*)&map, (void*)&P};
-  return cudaLaunchKernel((const void*)kernel, dim3(grid), dim3(TG * PSPLIT), args, smem, stream);
-}
-
-template <int TG, int PSPLIT, int DT, int MIXW, int MINB>
-static cudaError_t launchSpecT(const CUtensorMap& map, TmaParams& P, size_t smem, int dev, int smCount,
-                               cudaStream_t stream) noexcept {
-  static std::atomic<size_t> configured[64];
-  auto kernel = firTmaNcoSpecKernel<TG, PSPLIT, DT, MIXW, MINB>;
-  constexpr int kThreads = TG * PSPLIT + 32 * MIXW;
-  if (smem > configured[dev & 63].load(std::memory_order_acquire)) {
-    cudaError_t st = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (st != cudaSuccess) return report(st, "cudaFuncSetAttribute(MaxDynamicSharedMemorySize)");
-    configured[dev & 63].store(smem, std::memory_order_release);
-  }
-  int perSm = 0;
-  cudaError_t st = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, kernel, kThreads, smem);
-  if (st != cudaSuccess) return report(st, "cudaOccupancyMaxActiveBlocksPerMultiprocessor");
-  if (perSm < 1) return cudaErrorInvalidConfiguration;
-  {
-    const int warpsPerCta = kThreads / 32;
-    int balanced = perSm;
-    while (balanced > 1 && (balanced * warpsPerCta) % 4 != 0) balanced--;
-    if ((balanced * warpsPerCta) % 4 == 0) perSm = balanced;
-  }
-  const unsigned long long resident = (unsigned long long)perSm * (unsigned)smCount;
-  const unsigned grid = (unsigned)(P.totalTiles < resident ? P.totalTiles : resident);
-  P.strideChan = grid / P.tilesPerChannel;
-  P.strideTile = grid % P.tilesPerChannel;
-  void* args[] = {(void*)&map, (void*)&P};
-  return cudaLaunchKernel((const void*)kernel, dim3(grid), dim3(kThreads), args, smem, stream);
-}
-
-template <int DT>
-static cudaError_t launchSpecD(int variant, const CUtensorMap& map, TmaParams& P, size_t smem, int dev, int smCount,
-                               cudaStream_t stream) noexcept {
-  switch (variant) {
-#define X(id, tg, ps, mw, mb) \
-  case id: return launchSpecT<tg, ps, DT, mw, mb>(map, P, smem, dev, smCount, stream);
-    GSDR_SPEC_VARIANTS(X)
-#undef X
-    default: return cudaErrorInvalidValue;
-  }
-}
-
 static cudaError_t launchSpec(int variant, bool staticD, const CUtensorMap& map, TmaParams& P, size_t smem, int dev,
                               int smCount, cudaStream_t stream) noexcept {
   if (staticD) {
     switch (P.D) {
-      case 8: return launchSpecD<8>(variant, map, P, smem, dev, smCount, stream);
-      case 10: return launchSpecD<10>(variant, map, P, smem, dev, smCount, stream);
-      case 32: return launchSpecD<32>(variant, map, P, smem, dev, smCount, stream);
+      case 8: return launchSpecDt8(variant, map, P, smem, dev, smCount, stream);
+      case 10: return launchSpecDt10(variant, map, P, smem, dev, smCount, stream);
+      case 32: return launchSpecDt32(variant, map, P, smem, dev, smCount, stream);
       default: break;
     }
   }
-  return launchSpecD<0>(variant, map, P, smem, dev, smCount, stream);
-}
-
-template <int MODE, int DT>
-static cudaError_t launchTmaModeD(int variant, const CUtensorMap& map, TmaParams& P, size_t smem, int dev,
-                                  int smCount, cudaStream_t stream) noexcept {
-  switch (variant) {
-#define X(id, tg, ps, nb, mb) \
-  case id: return launchTmaT<MODE, tg, ps, DT, nb, mb>(map, P, smem, dev, smCount, stream);
-    GSDR_TMA_VARIANTS(X)
-#undef X
-    default: return cudaErrorInvalidValue;
-  }
+  return launchSpecDt0(variant, map, P, smem, dev, smCount, stream);
 }
 
 template <int MODE>
@@ -436,14 +262,14 @@ static cudaError_t launchTmaMode(int variant, bool staticD, const CUtensorMap& m
                                  int dev, int smCount, cudaStream_t stream) noexcept {
   if (staticD) {
     switch (P.D) {
-      case 4: return launchTmaModeD<MODE, 4>(variant, map, P, smem, dev, smCount, stream);
-      case 8: return launchTmaModeD<MODE, 8>(variant, map, P, smem, dev, smCount, stream);
-      case 10: return launchTmaModeD<MODE, 10>(variant, map, P, smem, dev, smCount, stream);
-      case 32: return launchTmaModeD<MODE, 32>(variant, map, P, smem, dev, smCount, stream);
+      case 4: return launchTmaDt4(MODE, variant, map, P, smem, dev, smCount, stream);
+      case 8: return launchTmaDt8(MODE, variant, map, P, smem, dev, smCount, stream);
+      case 10: return launchTmaDt10(MODE, variant, map, P, smem, dev, smCount, stream);
+      case 32: return launchTmaDt32(MODE, variant, map, P, smem, dev, smCount, stream);
       default: break;
     }
   }
-  return launchTmaModeD<MODE, 0>(variant, map, P, smem, dev, smCount, stream);
+  return launchTmaDt0(MODE, variant, map, P, smem, dev, smCount, stream);
 }
 
 // TMA-kernel variant ids: [0, kNumTmaVariants) = firTmaKernel, then the warp-specialised fused-NCO kernel.
@@ -541,46 +367,6 @@ static bool ccGeometry(const TmaVariant& v, size_t D, size_t T, TmaGeom* g) noex
   g->smemBytes = 1024 + (size_t)v.nbuf * (8 * D / tmaSegBytes((unsigned)D)) * 8 * (size_t)g->planeBytes +
                  2 * (size_t)(v.psplit - 1) * v.tg * 64 + 2 * (D * g->Jpad + 32) * 4;
   return true;
-}
-
-template <int TG, int PSPLIT, int DT, int NBUF, int MINB>
-static cudaError_t launchCcT(const CUtensorMap& map, TmaParams& P, size_t smem, int dev, int smCount,
-                             cudaStream_t stream) noexcept {
-  static std::atomic<size_t> configured[64];
-  auto kernel = firTmaCcKernel<TG, PSPLIT, DT, NBUF, MINB>;
-  if (smem > configured[dev & 63].load(std::memory_order_acquire)) {
-    cudaError_t st = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (st != cudaSuccess) return report(st, "cudaFuncSetAttribute(MaxDynamicSharedMemorySize)");
-    configured[dev & 63].store(smem, std::memory_order_release);
-  }
-  int perSm = 0;
-  cudaError_t st = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, kernel, TG * PSPLIT, smem);
-  if (st != cudaSuccess) return report(st, "cudaOccupancyMaxActiveBlocksPerMultiprocessor");
-  if (perSm < 1) return cudaErrorInvalidConfiguration;
-  {
-    const int warpsPerCta = (TG * PSPLIT) / 32;
-    int balanced = perSm;
-    while (balanced > 1 && (balanced * warpsPerCta) % 4 != 0) balanced--;
-    if ((balanced * warpsPerCta) % 4 == 0) perSm = balanced;
-  }
-  const unsigned long long resident = (unsigned long long)perSm * (unsigned)smCount;
-  const unsigned grid = (unsigned)(P.totalTiles < resident ? P.totalTiles : resident);
-  P.strideChan = grid / P.tilesPerChannel;
-  P.strideTile = grid % P.tilesPerChannel;
-  void* args[] = {(void*)&map, (void*)&P};
-  return cudaLaunchKernel((const void*)kernel, dim3(grid), dim3(TG * PSPLIT), args, smem, stream);
-}
-
-template <int DT>
-static cudaError_t launchCcD(int variant, const CUtensorMap& map, TmaParams& P, size_t smem, int dev, int smCount,
-                             cudaStream_t stream) noexcept {
-  switch (variant) {
-#define X(id, tg, ps, nb, mb) \
-  case id: return launchCcT<tg, ps, DT, nb, mb>(map, P, smem, dev, smCount, stream);
-    GSDR_CC_VARIANTS(X)
-#undef X
-    default: return cudaErrorInvalidValue;
-  }
 }
 
 static int firstCcVariantId() noexcept { return kNumVariants + kNumTmaVariants + kNumSpecVariants + kNumRealVariants; }
@@ -682,8 +468,8 @@ static cudaError_t launchTma(const FirCall& c, int variant, const TmaGeom& geom,
     if (tmaRows < 8) P.tmaRows = 0;
   }
   if (ccVariant >= 0) {
-    if (geom.staticD && D == 8) return launchCcD<8>(ccVariant, map, P, geom.smemBytes, dev, smCount, stream);
-    return launchCcD<0>(ccVariant, map, P, geom.smemBytes, dev, smCount, stream);
+    if (geom.staticD && D == 8) return launchCcDt8(ccVariant, map, P, geom.smemBytes, dev, smCount, stream);
+    return launchCcDt0(ccVariant, map, P, geom.smemBytes, dev, smCount, stream);
   }
   if (mixw > 0) {
     return launchSpec(variant - kNumTmaVariants, geom.staticD, map, P, geom.smemBytes, dev, smCount, stream);
@@ -733,46 +519,6 @@ static bool realGeometry(const RealVariant& v, size_t Dreal, size_t T, RealGeom*
   g->smemBytes = (size_t)v.nwin * (8 * D / G) * 8 * (size_t)g->planeBytes + 2 * (size_t)(v.psplit - 1) * v.tg * 64 +
                  (D * Jpad + 32) * 4 + (size_t)v.nraw * rawFloats * 4;
   return true;
-}
-
-template <int TG, int PSPLIT, int DT, int MIXW, int NWIN, int NRAW, int MINB>
-static cudaError_t launchRealT(RealParams& P, size_t smem, int dev, int smCount, cudaStream_t stream) noexcept {
-  static std::atomic<size_t> configured[64];
-  auto kernel = firTmaRealKernel<TG, PSPLIT, DT, MIXW, NWIN, NRAW, MINB>;
-  constexpr int kThreads = TG * PSPLIT + 32 * MIXW;
-  if (smem > configured[dev & 63].load(std::memory_order_acquire)) {
-    cudaError_t st = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (st != cudaSuccess) return report(st, "cudaFuncSetAttribute(MaxDynamicSharedMemorySize)");
-    configured[dev & 63].store(smem, std::memory_order_release);
-  }
-  int perSm = 0;
-  cudaError_t st = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, kernel, kThreads, smem);
-  if (st != cudaSuccess) return report(st, "cudaOccupancyMaxActiveBlocksPerMultiprocessor");
-  if (perSm < 1) return cudaErrorInvalidConfiguration;
-  {
-    const int warpsPerCta = kThreads / 32;
-    int balanced = perSm;
-    while (balanced > 1 && (balanced * warpsPerCta) % 4 != 0) balanced--;
-    if ((balanced * warpsPerCta) % 4 == 0) perSm = balanced;
-  }
-  const unsigned long long resident = (unsigned long long)perSm * (unsigned)smCount;
-  const unsigned grid = (unsigned)(P.totalTiles < resident ? P.totalTiles : resident);
-  P.strideChan = grid / P.tilesPerChannel;
-  P.strideTile = grid % P.tilesPerChannel;
-  void* args[] = {(void*)&P};
-  return cudaLaunchKernel((const void*)kernel, dim3(grid), dim3(kThreads), args, smem, stream);
-}
-
-template <int DT>
-static cudaError_t launchRealD(int variant, RealParams& P, size_t smem, int dev, int smCount,
-                               cudaStream_t stream) noexcept {
-  switch (variant) {
-#define X(id, tg, ps, mw, nw, nr, mb) \
-  case id: return launchRealT<tg, ps, DT, mw, nw, nr, mb>(P, smem, dev, smCount, stream);
-    GSDR_REAL_VARIANTS(X)
-#undef X
-    default: return cudaErrorInvalidValue;
-  }
 }
 
 static bool realVariantFits(int id, const FirCall& c, int maxSmem, RealGeom* geom) noexcept {
@@ -845,12 +591,12 @@ static cudaError_t launchReal(const FirCall& c, int variant, const RealGeom& geo
   P.dbg = (unsigned)gDebugFlags.load(std::memory_order_relaxed);
   if (geom.staticD) {
     switch (D) {
-      case 2: return launchRealD<2>(variant, P, geom.smemBytes, dev, smCount, stream);
-      case 10: return launchRealD<10>(variant, P, geom.smemBytes, dev, smCount, stream);
+      case 2: return launchRealDt2(variant, P, geom.smemBytes, dev, smCount, stream);
+      case 10: return launchRealDt10(variant, P, geom.smemBytes, dev, smCount, stream);
       default: break;
     }
   }
-  return launchRealD<0>(variant, P, geom.smemBytes, dev, smCount, stream);
+  return launchRealDt0(variant, P, geom.smemBytes, dev, smCount, stream);
 }
 
 template <class IN_T, class OUT_T, class TAP_T>
