@@ -12,14 +12,17 @@ from .api import (  # noqa: F401
     fir_num_inputs,
     fir_num_outputs,
     gsdrAdjustFrequencyFirFC,
+    gsdrAdjustFrequencyFirFCInt8,
     gsdrAdjustFrequencyFirFCLiteral,
     gsdrFirCC,
     gsdrFirCF,
     gsdrFirFC,
     gsdrFirFCBatched,
+    gsdrFirFCInt8,
     gsdrFirFF,
     gsdrFirFFBatched,
     gsdrFmDemod,
+    gsdrInt8ToNormFloat,
     gsdrQuadAmDemod,
     gsdrQuadFmDemod,
     nco_phase_step,

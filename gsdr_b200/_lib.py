@@ -92,6 +92,10 @@ SIGNATURES = {
                                                    c_void_p, c_void_p, c_size_t]),
     "gsdrFirFCMultiGpuHost": (cudaError_t, [C.POINTER(c_void_p), C.c_int, c_size_t, c_void_p, c_size_t, c_void_p,
                                             c_void_p, c_size_t]),
+    # include/gsdr/conversion.h
+    "gsdrInt8ToNormFloat": (cudaError_t, [c_void_p, c_void_p, c_size_t, c_int32, c_void_p]),
+    "gsdrFirFCInt8": (cudaError_t, _FIR_ARGS),
+    "gsdrAdjustFrequencyFirFCInt8": (cudaError_t, _NCO_ARGS),
     # include/gsdr/stream.h
     "gsdrFirStreamPlan": (C.c_int, [C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint32,
                                     C.POINTER(StreamPlan)]),

@@ -81,6 +81,15 @@ gsdrAdjustFrequencyFirFC = _nco("gsdrAdjustFrequencyFirFC")
 gsdrAdjustFrequencyFirFCLiteral = _nco("gsdrAdjustFrequencyFirFCLiteral")
 
 
+gsdrFirFCInt8 = _fir("gsdrFirFCInt8")
+gsdrAdjustFrequencyFirFCInt8 = _nco("gsdrAdjustFrequencyFirFCInt8")
+
+
+def gsdrInt8ToNormFloat(input, output, numElements, cudaDevice=0, cudaStream=None):
+    _check(lib.gsdrInt8ToNormFloat(_ptr(input), _ptr(output), numElements, cudaDevice, _stream(cudaStream)),
+           "gsdrInt8ToNormFloat")
+
+
 def gsdrQuadFmDemod(input, output, gain, numOutputElements, cudaDevice=0, cudaStream=None):
     _check(lib.gsdrQuadFmDemod(_ptr(input), _ptr(output), gain, numOutputElements, cudaDevice, _stream(cudaStream)),
            "gsdrQuadFmDemod")

@@ -563,4 +563,59 @@ __global__ void __launch_bounds__(kDirectThreads) firDirectNcoKernel(const Direc
   if (live) P.y[(size_t)chan * P.yStride + n] = acc;
 }
 
+// Direct kernel for int8 IQ input (any D / T / alignment): conversion (ref: src/conversion.cu:26) and the optional
+// exact NCO per tap; the fallback of firTmaInt8Kernel.
+struct DirectInt8Params {
+  const signed char* x;  // interleaved I, Q
+  const float* h;
+  float2* y;
+  unsigned long long nOut, D, T;
+  unsigned long long xStride, yStride;  // in samples / outputs
+  unsigned blocksPerChannel;
+  unsigned long long ncoStep, ncoFirst;
+};
+
+template <bool NCO>
+__global__ void __launch_bounds__(kDirectThreads) firDirectInt8Kernel(const DirectInt8Params P) {
+  __shared__ float hs[kDirectTapChunk];
+  const unsigned chan = blockIdx.x / P.blocksPerChannel;
+  const unsigned blk = blockIdx.x - chan * P.blocksPerChannel;
+  const unsigned long long n = (unsigned long long)blk * kDirectThreads + threadIdx.x;
+  const bool live = n < P.nOut;
+  const unsigned long long s0 = live ? n * P.D : 0ull;
+  const signed char* x = P.x + 2u * ((size_t)chan * P.xStride + s0);
+  float2 acc = make_float2(0.0f, 0.0f);
+  for (unsigned long long t0 = 0; t0 < P.T; t0 += kDirectTapChunk) {
+    const unsigned cnt = (unsigned)((P.T - t0 < (unsigned long long)kDirectTapChunk) ? (P.T - t0) : kDirectTapChunk);
+    __syncthreads();
+    for (unsigned i = threadIdx.x; i < cnt; i += kDirectThreads) hs[i] = P.h[t0 + i];
+    __syncthreads();
+    if (live) {
+      const signed char* xp = x + 2u * t0;
+      unsigned long long phase = (P.ncoFirst + s0 + t0) * P.ncoStep;
+      for (unsigned i = 0; i < cnt; i++) {
+        float re = fmaxf(-1.0f, __fdiv_rn((float)xp[2 * i], 127.0f));
+        float im = fmaxf(-1.0f, __fdiv_rn((float)xp[2 * i + 1], 127.0f));
+        if (NCO) {
+          float sn, cs;
+          sincospif((float)(int)(unsigned)(phase >> 32) * 4.656612873077392578125e-10f, &sn, &cs);
+          phase += P.ncoStep;
+          const float mre = __fmaf_rn(re, cs, -__fmul_rn(im, sn));
+          const float mim = __fmaf_rn(re, sn, __fmul_rn(im, cs));
+          re = mre, im = mim;
+        }
+        acc.x = __fmaf_rn(hs[i], re, acc.x);
+        acc.y = __fmaf_rn(hs[i], im, acc.y);
+      }
+    }
+  }
+  if (live) P.y[(size_t)chan * P.yStride + n] = acc;
+}
+
+// ref: src/conversion.cu:20-27 (k_int8ToFloat), with the bounds check the reference gets wrong (x > numElements)
+static __global__ void int8ToNormFloatKernel(const signed char* in, float* out, unsigned long long n) {
+  const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = fmaxf(-1.0f, __fdiv_rn((float)in[i], 127.0f));
+}
+
 }  // namespace gsdr_b200

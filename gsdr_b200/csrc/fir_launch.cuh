@@ -267,6 +267,59 @@ static cudaError_t launchRealD(int variant, RealParams& P, size_t smem, int dev,
   }
 }
 
+// int8-input kernel (firTmaInt8Kernel): X(id, TG, PSPLIT, MIXW, MINB)
+#define GSDR_INT8_VARIANTS(X) \
+  X(0, 64, 2, 4, 2)           \
+  X(1, 32, 4, 4, 1)           \
+  X(2, 32, 2, 2, 4)
+
+static constexpr SpecVariant kInt8Variants[] = {
+#define X(id, tg, ps, mw, mb) {tg, ps, mw, mb},
+    GSDR_INT8_VARIANTS(X)
+#undef X
+};
+static constexpr int kNumInt8Variants = (int)(sizeof(kInt8Variants) / sizeof(kInt8Variants[0]));
+
+template <int TG, int PSPLIT, int DT, int MIXW, bool NCO, int MINB>
+static cudaError_t launchInt8T(Int8Params& P, size_t smem, int dev, int smCount, cudaStream_t stream) noexcept {
+  static std::atomic<size_t> configured[64];
+  auto kernel = firTmaInt8Kernel<TG, PSPLIT, DT, MIXW, NCO, MINB>;
+  constexpr int kThreads = TG * PSPLIT + 32 * MIXW;
+  if (smem > configured[dev & 63].load(std::memory_order_acquire)) {
+    cudaError_t st = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (st != cudaSuccess) return report(st, "cudaFuncSetAttribute(MaxDynamicSharedMemorySize)");
+    configured[dev & 63].store(smem, std::memory_order_release);
+  }
+  int perSm = 0;
+  cudaError_t st = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, kernel, kThreads, smem);
+  if (st != cudaSuccess) return report(st, "cudaOccupancyMaxActiveBlocksPerMultiprocessor");
+  if (perSm < 1) return cudaErrorInvalidConfiguration;
+  {
+    const int warpsPerCta = kThreads / 32;
+    int balanced = perSm;
+    while (balanced > 1 && (balanced * warpsPerCta) % 4 != 0) balanced--;
+    if ((balanced * warpsPerCta) % 4 == 0) perSm = balanced;
+  }
+  const unsigned long long resident = (unsigned long long)perSm * (unsigned)smCount;
+  const unsigned grid = (unsigned)(P.totalTiles < resident ? P.totalTiles : resident);
+  P.strideChan = grid / P.tilesPerChannel;
+  P.strideTile = grid % P.tilesPerChannel;
+  void* args[] = {(void*)&P};
+  return cudaLaunchKernel((const void*)kernel, dim3(grid), dim3(kThreads), args, smem, stream);
+}
+
+template <int DT, bool NCO>
+static cudaError_t launchInt8D(int variant, Int8Params& P, size_t smem, int dev, int smCount,
+                               cudaStream_t stream) noexcept {
+  switch (variant) {
+#define X(id, tg, ps, mw, mb) \
+  case id: return launchInt8T<tg, ps, DT, mw, NCO, mb>(P, smem, dev, smCount, stream);
+    GSDR_INT8_VARIANTS(X)
+#undef X
+    default: return cudaErrorInvalidValue;
+  }
+}
+
 // ---- per-decimation entry points (fir_inst_*.cu); mode is a PolyMode ----
 #define GSDR_TMA_ARGS const CUtensorMap &map, TmaParams &P, size_t smem, int dev, int smCount, cudaStream_t stream
 #define GSDR_REAL_ARGS RealParams &P, size_t smem, int dev, int smCount, cudaStream_t stream
@@ -279,6 +332,14 @@ GSDR_DECLARE_TMA_DT(0) GSDR_DECLARE_TMA_DT(4) GSDR_DECLARE_TMA_DT(8) GSDR_DECLAR
 GSDR_DECLARE_SPEC_DT(0) GSDR_DECLARE_SPEC_DT(8) GSDR_DECLARE_SPEC_DT(10) GSDR_DECLARE_SPEC_DT(32)
 GSDR_DECLARE_CC_DT(0) GSDR_DECLARE_CC_DT(8)
 GSDR_DECLARE_REAL_DT(0) GSDR_DECLARE_REAL_DT(2) GSDR_DECLARE_REAL_DT(10)
+#define GSDR_INT8_ARGS Int8Params &P, size_t smem, int dev, int smCount, cudaStream_t stream
+#define GSDR_DECLARE_INT8_DT(DT) cudaError_t launchInt8Dt##DT(bool nco, int variant, GSDR_INT8_ARGS) noexcept;
+GSDR_DECLARE_INT8_DT(0) GSDR_DECLARE_INT8_DT(8) GSDR_DECLARE_INT8_DT(10)
+#define GSDR_DEFINE_INT8_DT(DT)                                                             \
+  cudaError_t launchInt8Dt##DT(bool nco, int variant, GSDR_INT8_ARGS) noexcept {            \
+    return nco ? launchInt8D<DT, true>(variant, P, smem, dev, smCount, stream)              \
+               : launchInt8D<DT, false>(variant, P, smem, dev, smCount, stream);            \
+  }
 
 #define GSDR_DEFINE_TMA_DT(DT)                                                                                  \
   cudaError_t launchTmaDt##DT(int mode, int variant, GSDR_TMA_ARGS) noexcept {                                  \

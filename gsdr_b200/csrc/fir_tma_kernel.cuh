@@ -1171,4 +1171,226 @@ __global__ void __launch_bounds__(TG* PSPLIT, MINB)
   asm volatile("cp.async.wait_group 0;\n" ::: "memory");
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// int8 IQ input (the conversion of ref: src/conversion.cu:20-27 fused into the staging):
+//     x[k] = (conv(I[k]), conv(Q[k])),  conv(v) = max(-1, v / 127)        (interleaved int8 I, Q in HBM: 2 bytes / sample)
+//     out[n] = sum_i x[nD + i] * [phasor(first + nD + i)] * h[i]
+// Producer warps bulk-copy the raw bytes of a tile's window (a quarter of the float traffic), convert them, optionally
+// apply the exact NCO (anchor per row x per-CTA rotation table, as in tmaMixWindow) and write the plane layout; filter
+// warps run firComputePairs.  conv(v) = max(v, -127) / 127 exactly, and the division by 127 is folded into the taps
+// (staged as h[i] / 127): one rounding per tap instead of one per sample — within the FP32 tolerance of
+// convert-then-filter, not bit-identical to it.  Hand-over as in firTmaRealKernel (rawBar / fullMix / empty).
+// ---------------------------------------------------------------------------------------------------------
+struct Int8Params : TmaParams {
+  unsigned rawBytes;  // bytes of input one tile reads, a multiple of 16
+  float tapScale;     // 1 / 127
+};
+
+// the four int8 of w (already XORed with 0x80808080: offset binary) -> floats, clamped to >= -127
+__device__ __forceinline__ float4 int8x4ToFloat(unsigned wBiased) {
+  float4 r;
+  // byte k into the mantissa of 2^23: 0x4B000000 | u  ==  8388608 + u;  u - 128 = the signed value
+  r.x = __uint_as_float(__byte_perm(wBiased, 0x4B000000u, 0x7650)) - 8388736.0f;
+  r.y = __uint_as_float(__byte_perm(wBiased, 0x4B000000u, 0x7651)) - 8388736.0f;
+  r.z = __uint_as_float(__byte_perm(wBiased, 0x4B000000u, 0x7652)) - 8388736.0f;
+  r.w = __uint_as_float(__byte_perm(wBiased, 0x4B000000u, 0x7653)) - 8388736.0f;
+  r.x = fmaxf(r.x, -127.0f);
+  r.y = fmaxf(r.y, -127.0f);
+  r.z = fmaxf(r.z, -127.0f);
+  r.w = fmaxf(r.w, -127.0f);
+  return r;
+}
+
+template <int TG, int PSPLIT, int DT, int MIXW, bool NCO, int MINB>
+__global__ void __launch_bounds__(TG* PSPLIT + 32 * MIXW, MINB) firTmaInt8Kernel(const Int8Params P) {
+  constexpr unsigned NTF = TG * PSPLIT;  // filter threads
+  constexpr unsigned NTM = 32 * MIXW;    // producer threads
+  constexpr unsigned BOUT = kTmaR * TG;
+  extern __shared__ __align__(16) unsigned char smemRaw[];
+  __shared__ __align__(8) unsigned long long rawBar[2], fullMix[2], emptyBar[2];
+  const unsigned D = DT ? (unsigned)DT : P.D;
+  const unsigned rowBytes = 8u * D;
+  const unsigned segBytes = DT ? tmaSegBytes(DT ? DT : 2) : P.segBytes;
+  const unsigned numSegs = rowBytes / segBytes;
+  const unsigned planeBytes =
+      DT ? tmaPlaneRows(TG, kTmaJpadCap, DT ? DT : 2) * segBytes + kRealPlanePad : P.planeBytes;
+  const unsigned bufBytes = numSegs * 8u * planeBytes;
+  unsigned char* bufBase = smemRaw;
+  float4* scratch = reinterpret_cast<float4*>(bufBase + 2u * bufBytes);
+  float* hs = reinterpret_cast<float*>(scratch + 2u * (PSPLIT - 1) * (kTmaR / 2) * TG);
+  float2* ncoA = reinterpret_cast<float2*>(hs + (size_t)D * P.Jpad + 32u);  // row anchors of the window being built
+  float2* ncoR = ncoA + (BOUT + P.Jpad);                                     // exp(j*p*step), p < D
+  unsigned char* raw = reinterpret_cast<unsigned char*>(ncoR + D + (D & 1u));  // 2 x rawBytes, 16-byte aligned
+
+  const unsigned tid = threadIdx.x;
+  const unsigned rowsStaged = BOUT + P.Jpad;
+  if (tid == 0) {
+    for (int b = 0; b < 2; b++) {
+      mbarInit(&rawBar[b], 1);
+      mbarInit(&fullMix[b], NTM);
+      mbarInit(&emptyBar[b], NTF);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (NCO) {
+    for (unsigned p = tid; p < D; p += NTF + NTM) ncoR[p] = ncoExactPhasor((unsigned long long)p, P.ncoStep);
+  }
+  {
+    const unsigned nh = D * P.Jpad;
+    for (unsigned i = tid; i < nh + 32u; i += NTF + NTM) {
+      const unsigned pp = i / (2u * P.Jpad);
+      const unsigned rem = i - pp * 2u * P.Jpad;
+      const unsigned ti = (rem >> 1) * D + 2u * pp + (rem & 1u);
+      hs[i] = (i < nh && ti < P.T) ? __ldg(P.h + ti) * P.tapScale : 0.0f;
+    }
+  }
+  __syncthreads();
+
+  unsigned chan = blockIdx.x / P.tilesPerChannel;
+  unsigned tile = blockIdx.x - chan * P.tilesPerChannel;
+  auto advance = [&](unsigned& c, unsigned& tl) {
+    c += P.strideChan;
+    tl += P.strideTile;
+    if (tl >= P.tilesPerChannel) {
+      tl -= P.tilesPerChannel;
+      c += 1;
+    }
+  };
+
+  if (tid >= NTF) {
+    // ===================== producer warps =====================
+    const unsigned lt = tid - NTF;
+    const unsigned char* xb = reinterpret_cast<const unsigned char*>(P.x);  // 2 bytes per sample
+    auto tileIsFast = [&](unsigned tl) -> bool {
+      return (unsigned long long)tl * BOUT * D + (P.rawBytes >> 1) <= P.nIn;
+    };
+    auto issueRaw = [&](unsigned c, unsigned tl, unsigned rb) {
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      mbarExpectTx(&rawBar[rb], P.rawBytes);
+      bulkLoad1d(raw + (size_t)rb * P.rawBytes, xb + 2u * ((size_t)c * P.xStride + (size_t)tl * BOUT * D), P.rawBytes,
+                 &rawBar[rb]);
+    };
+    if (lt == 0 && chan < P.numChannels && tileIsFast(tile)) issueRaw(chan, tile, 0);
+    for (unsigned k = 0; chan < P.numChannels; k++) {
+      unsigned nextChan = chan, nextTile = tile;
+      advance(nextChan, nextTile);
+      const unsigned b = k & 1u;
+      if (lt == 0 && nextChan < P.numChannels && tileIsFast(nextTile)) issueRaw(nextChan, nextTile, b ^ 1u);
+      if (k >= 2) mbarWait(&emptyBar[b], ((k >> 1) - 1u) & 1u);
+      unsigned char* rawb = raw + (size_t)b * P.rawBytes;
+      const unsigned long long in0 = (unsigned long long)tile * BOUT * D;
+      if (tileIsFast(tile)) {
+        mbarWait(&rawBar[b], (k >> 1) & 1u);
+      } else {
+        if (lt == 0) mbarArrive(&rawBar[b]);
+        const unsigned short* xc = reinterpret_cast<const unsigned short*>(xb) + (size_t)chan * P.xStride;
+        unsigned short* r16 = reinterpret_cast<unsigned short*>(rawb);
+        for (unsigned i = lt; i < (P.rawBytes >> 1); i += NTM) {
+          const unsigned long long g = in0 + i;
+          r16[i] = (g < P.nIn) ? __ldg(xc + g) : (unsigned short)0;
+        }
+        mixBarrier<NTM, 1>();
+      }
+      unsigned char* buf = bufBase + b * bufBytes;
+      if (NCO) {
+        const unsigned mhCount = rowsStaged >> 3;
+        for (unsigned m = lt; m < rowsStaged; m += NTM) {
+          ncoA[(m & 7u) * mhCount + (m >> 3)] = ncoExactPhasor(P.ncoFirst + in0 + (unsigned long long)m * D, P.ncoStep);
+        }
+        mixBarrier<NTM, 1>();
+      }
+      // work item = (row m, branch pair pp): 4 raw bytes -> two converted (and mixed) samples -> one float4
+      {
+        const unsigned pairsPerRow = D >> 1;
+        const unsigned total = rowsStaged * pairsPerRow;
+        unsigned m = lt / pairsPerRow, pp = lt - m * pairsPerRow;
+        const unsigned dm = NTM / pairsPerRow, dpp = NTM - dm * pairsPerRow;
+        const unsigned mhCount = rowsStaged >> 3;
+        for (unsigned e = lt; e < total; e += NTM) {
+          const unsigned w = *reinterpret_cast<const unsigned*>(rawb + 4u * e) ^ 0x80808080u;
+          float4 v = int8x4ToFloat(w);
+          if (NCO) {
+            const float2 an = ncoA[(m & 7u) * mhCount + (m >> 3)];
+            const float4 rr = *reinterpret_cast<const float4*>(ncoR + 2u * pp);
+            const float2 w0 = cmulf(an, make_float2(rr.x, rr.y));
+            const float2 w1 = cmulf(an, make_float2(rr.z, rr.w));
+            const float2 a = cmulf(make_float2(v.x, v.y), w0);
+            const float2 c = cmulf(make_float2(v.z, v.w), w1);
+            v = make_float4(a.x, a.y, c.x, c.y);
+          }
+          *reinterpret_cast<float4*>(buf + tmaSampleOffset<DT>(m, 2u * pp, planeBytes, P)) = v;
+          m += dm;
+          pp += dpp;
+          if (pp >= pairsPerRow) {
+            pp -= pairsPerRow;
+            m += 1;
+          }
+        }
+      }
+      mbarArrive(&fullMix[b]);
+      mixBarrier<NTM, 1>();  // raw buffer b and the anchors may be overwritten
+      chan = nextChan;
+      tile = nextTile;
+    }
+    return;
+  }
+
+  // ============================== filter warps ==============================
+  const unsigned grp = tid / TG;
+  const unsigned t = tid - grp * TG;
+  const unsigned numPairs = D >> 1;
+  const unsigned ppBegin = (grp * numPairs) / PSPLIT;
+  const unsigned ppEnd = ((grp + 1) * numPairs) / PSPLIT;
+  for (unsigned k = 0; chan < P.numChannels; k++, advance(chan, tile)) {
+    const unsigned b = k & 1u;
+    const unsigned char* buf = bufBase + b * bufBytes;
+    const unsigned long long o0 = (unsigned long long)tile * BOUT;
+    mbarWait(&fullMix[b], (k >> 1) & 1u);
+    float2 acc[kTmaR];
+#pragma unroll
+    for (int r = 0; r < kTmaR; r++) acc[r] = make_float2(0.0f, 0.0f);
+    if (ppBegin < ppEnd) firComputePairs<DT>(acc, buf, hs, t, ppBegin, ppEnd, P.Jpad, planeBytes, P);
+    mbarArrive(&emptyBar[b]);
+    if (PSPLIT > 1) {
+      float4* red = scratch + (size_t)(k & 1u) * (PSPLIT - 1) * (kTmaR / 2) * TG;
+      if (grp > 0) {
+#pragma unroll
+        for (int q = 0; q < kTmaR / 2; q++) {
+          red[((grp - 1) * (kTmaR / 2) + q) * TG + t] =
+              make_float4(acc[2 * q].x, acc[2 * q].y, acc[2 * q + 1].x, acc[2 * q + 1].y);
+        }
+      }
+      asm volatile("bar.sync 2, %0;" ::"n"(NTF) : "memory");
+      if (grp == 0) {
+#pragma unroll
+        for (int g = 1; g < PSPLIT; g++) {
+#pragma unroll
+          for (int q = 0; q < kTmaR / 2; q++) {
+            const float4 v = red[((g - 1) * (kTmaR / 2) + q) * TG + t];
+            acc[2 * q].x += v.x;
+            acc[2 * q].y += v.y;
+            acc[2 * q + 1].x += v.z;
+            acc[2 * q + 1].y += v.w;
+          }
+        }
+      }
+    }
+    if (grp == 0) {
+      const unsigned long long ob = o0 + (unsigned long long)t * kTmaR;
+      float2* y = P.y + (size_t)chan * P.yStride;
+      if (P.y16 && ob + kTmaR <= P.nOut) {
+#pragma unroll
+        for (int r = 0; r < kTmaR; r += 2) {
+          *reinterpret_cast<float4*>(y + ob + r) = make_float4(acc[r].x, acc[r].y, acc[r + 1].x, acc[r + 1].y);
+        }
+      } else {
+#pragma unroll
+        for (int r = 0; r < kTmaR; r++) {
+          if (ob + r < P.nOut) y[ob + r] = acc[r];
+        }
+      }
+    }
+  }
+}
+
 }  // namespace gsdr_b200

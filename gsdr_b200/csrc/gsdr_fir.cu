@@ -3,6 +3,7 @@
 // ref: src/fm.cu:46-56).  No CPU fallback exists: every path ends in a kernel launch on the caller's stream.
 #include <gsdr/adjust_frequency.h>
 #include <gsdr/b200.h>
+#include <gsdr/conversion.h>
 #include <gsdr/fir.h>
 
 #include <atomic>
@@ -739,6 +740,93 @@ cudaError_t enqueueFir(const FirCall& c, cudaStream_t stream) noexcept {
   return cudaErrorInvalidValue;
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// int8 IQ input (<gsdr/conversion.h>): firTmaInt8Kernel, or the direct kernel when the call does not qualify
+// ---------------------------------------------------------------------------------------------------------
+static cudaError_t enqueueInt8(bool nco, float sampleRate, float frequencyShift, size_t firstSampleIndex,
+                               size_t decimation, const float* taps, size_t tapCount, const int8_t* input,
+                               cuComplex* output, size_t numOutputs, cudaStream_t stream) noexcept {
+  if (numOutputs == 0) return cudaSuccess;
+  if (decimation == 0) return cudaErrorInvalidValue;
+  if (tapCount == 0) return cudaMemsetAsync(output, 0, numOutputs * sizeof(cuComplex), stream);
+  int dev = 0;
+  cudaError_t st = cudaGetDevice(&dev);
+  if (st != cudaSuccess) return st;
+  const DeviceInfo* info = deviceInfo(dev);
+  if (!info || info->status != cudaSuccess) return info ? info->status : cudaErrorInvalidDevice;
+  const size_t D = decimation, T = tapCount;
+  const unsigned long long nIn = (unsigned long long)(numOutputs - 1) * D + T;
+  const int forced = gForcedVariant.load(std::memory_order_relaxed);
+
+  if (forced != -2 && tmaSupportedDecimation(D) && (uintptr_t)input % 16 == 0) {
+    const size_t J = (T + D - 1) / D;
+    const size_t Jpad = (J + 15) / 16 * 16;
+    const size_t G = tmaSegBytes((unsigned)D);
+    const bool staticD = (D == 8 || D == 10) && Jpad <= kTmaJpadCap;
+    static const int orderNarrow[] = {0, 2, 1};
+    static const int orderWide[] = {1, 0, 2};
+    const int* order = D > 16 ? orderWide : orderNarrow;
+    for (int k = 0; k < kNumInt8Variants; k++) {
+      const int id = order[k];
+      const SpecVariant& v = kInt8Variants[id];
+      if ((D / 2) < (size_t)v.psplit) continue;
+      const size_t mhp = tmaPlaneRows((unsigned)v.tg, (unsigned)(staticD ? kTmaJpadCap : Jpad), (unsigned)D);
+      const size_t planeBytes = mhp * G + kRealPlanePad;
+      const size_t rows = (size_t)kTmaR * v.tg + Jpad;
+      const size_t rawBytes = (rows * D * 2 + 15) / 16 * 16;
+      const size_t smem = 2 * (8 * D / G) * 8 * planeBytes + 2 * (size_t)(v.psplit - 1) * v.tg * 64 +
+                          (D * Jpad + 32) * 4 + (rows + D + 1) * 8 + 2 * rawBytes;
+      if (smem > (size_t)info->maxSmemOptin || rawBytes > 0xfffff0u) continue;
+      const size_t bout = (size_t)kTmaR * v.tg;
+      const unsigned long long tiles = (numOutputs + bout - 1) / bout;
+      if (tiles > 0x7fffffffull) break;
+      Int8Params P{};
+      P.x = (const float2*)input;
+      P.h = taps;
+      P.y = (float2*)output;
+      P.nOut = numOutputs;
+      P.nIn = nIn;
+      P.tilesPerChannel = (unsigned)tiles;
+      P.totalTiles = (unsigned)tiles;
+      P.numChannels = 1;
+      P.D = (unsigned)D;
+      P.T = (unsigned)T;
+      P.Jpad = (unsigned)Jpad;
+      P.rowBytes = (unsigned)(8 * D);
+      P.segBytes = (unsigned)G;
+      P.mhp = (unsigned)mhp;
+      P.planeBytes = (unsigned)planeBytes;
+      if (G == 32) P.swzShift = 2, P.swzMask = 1;
+      if (G == 64) P.swzShift = 1, P.swzMask = 3;
+      if (G == 128) P.swzShift = 0, P.swzMask = 7;
+      P.y16 = ((uintptr_t)output % 16 == 0) ? 1u : 0u;
+      P.ncoStep = ncoPhaseStep(frequencyShift, sampleRate);
+      P.ncoFirst = firstSampleIndex;
+      P.rawBytes = (unsigned)rawBytes;
+      P.tapScale = 1.0f / 127.0f;
+      if (staticD && D == 8) return launchInt8Dt8(nco, id, P, smem, dev, info->smCount, stream);
+      if (staticD && D == 10) return launchInt8Dt10(nco, id, P, smem, dev, info->smCount, stream);
+      return launchInt8Dt0(nco, id, P, smem, dev, info->smCount, stream);
+    }
+  }
+
+  DirectInt8Params P{};
+  P.x = (const signed char*)input;
+  P.h = taps;
+  P.y = (float2*)output;
+  P.nOut = numOutputs;
+  P.D = D;
+  P.T = T;
+  const unsigned long long bpc = (numOutputs + kDirectThreads - 1) / kDirectThreads;
+  if (bpc > 0x7fffffffull) return cudaErrorInvalidValue;
+  P.blocksPerChannel = (unsigned)bpc;
+  P.ncoStep = ncoPhaseStep(frequencyShift, sampleRate);
+  P.ncoFirst = firstSampleIndex;
+  void* args[] = {(void*)&P};
+  const void* kernel = nco ? (const void*)firDirectInt8Kernel<true> : (const void*)firDirectInt8Kernel<false>;
+  return cudaLaunchKernel(kernel, dim3((unsigned)bpc), dim3(kDirectThreads), args, 0, stream);
+}
+
 static cudaError_t firEntry(FirType type, size_t decimation, const void* taps, size_t tapCount, const void* input,
                             void* output, size_t numOutputs, int32_t cudaDevice, cudaStream_t stream) noexcept {
   DeviceScope scope(cudaDevice);
@@ -825,6 +913,40 @@ GSDR_C_LINKAGE cudaError_t gsdrAdjustFrequencyFirFCLiteral(float sampleRate, flo
 
 GSDR_C_LINKAGE uint64_t gsdrNcoPhaseStep(float frequencyShift, float sampleRate) GSDR_NO_EXCEPT {
   return ncoPhaseStep(frequencyShift, sampleRate);
+}
+
+// ---- <gsdr/conversion.h> ---------------------------------------------------------------------------------
+
+GSDR_C_LINKAGE cudaError_t gsdrInt8ToNormFloat(const int8_t* input, float* output, size_t numElements,
+                                               int32_t cudaDevice, cudaStream_t cudaStream) GSDR_NO_EXCEPT {
+  DeviceScope scope(cudaDevice);
+  if (scope.status() != cudaSuccess) return scope.status();
+  if (numElements == 0) return cudaSuccess;
+  const unsigned long long blocks = (numElements + 255) / 256;
+  if (blocks > 0x7fffffffull) return cudaErrorInvalidValue;
+  unsigned long long n = numElements;
+  const signed char* in = (const signed char*)input;
+  void* args[] = {(void*)&in, (void*)&output, (void*)&n};
+  return cudaLaunchKernel((const void*)int8ToNormFloatKernel, dim3((unsigned)blocks), dim3(256), args, 0, cudaStream);
+}
+
+GSDR_C_LINKAGE cudaError_t gsdrFirFCInt8(size_t decimation, const float* taps, size_t tapCount, const int8_t* input,
+                                         cuComplex* output, size_t numOutputs, int32_t cudaDevice,
+                                         cudaStream_t cudaStream) GSDR_NO_EXCEPT {
+  DeviceScope scope(cudaDevice);
+  if (scope.status() != cudaSuccess) return scope.status();
+  return enqueueInt8(false, 1.0f, 0.0f, 0, decimation, taps, tapCount, input, output, numOutputs, cudaStream);
+}
+
+GSDR_C_LINKAGE cudaError_t gsdrAdjustFrequencyFirFCInt8(float sampleRate, float frequencyShift,
+                                                        size_t firstSampleIndex, size_t decimation, const float* taps,
+                                                        size_t tapCount, const int8_t* input, cuComplex* output,
+                                                        size_t numOutputs, int32_t cudaDevice,
+                                                        cudaStream_t cudaStream) GSDR_NO_EXCEPT {
+  DeviceScope scope(cudaDevice);
+  if (scope.status() != cudaSuccess) return scope.status();
+  return enqueueInt8(true, sampleRate, frequencyShift, firstSampleIndex, decimation, taps, tapCount, input, output,
+                     numOutputs, cudaStream);
 }
 
 // ---- tuning / introspection hooks of <gsdr/b200.h> -------------------------------------------------------

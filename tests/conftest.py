@@ -39,3 +39,16 @@ def cuda_device():
     assert torch.cuda.is_available()
     torch.cuda.set_device(0)
     return torch.device("cuda:0")
+
+
+@pytest.fixture(autouse=True)
+def _auto_kernel_variant(request):
+    """GPU tests may force a kernel variant (gsdrB200SetKernelVariant is process-wide): reset it around every test."""
+    if "gpu" not in request.keywords:
+        yield
+        return
+    import gsdr_b200 as g
+
+    g.set_kernel_variant(-1)
+    yield
+    g.set_kernel_variant(-1)

@@ -43,13 +43,6 @@ def _run(kind, D, taps, x, n_out, dev, stream=None):
     return full[8:8 + n_out]
 
 
-@pytest.fixture(autouse=True)
-def _auto_variant():
-    g.set_kernel_variant(-1)
-    yield
-    g.set_kernel_variant(-1)
-
-
 @pytest.mark.parametrize("kind", ["ff", "fc", "cc", "cf"])
 @pytest.mark.parametrize("T,n_out", EDGE_SHAPES)
 @pytest.mark.parametrize("D", [1, 2, 5])

@@ -51,16 +51,23 @@ def main():
     real = args.kind == "ff"
     n_out = g.fir_num_outputs(n_in, T, D)
     x = synth.tone_plus_noise(0, n_in, seed=1, device=dev, real=real)
+    i8 = args.kind == "i8"
+    if i8:  # int8 IQ input: the same signal quantised to 8 bits, 2 bytes per sample
+        x = torch.view_as_real(x).mul(127.0).round().clamp(-127, 127).to(torch.int8).reshape(-1).contiguous()
     cc = args.kind == "cc"
     taps = torch.from_numpy(synth.random_taps(T, 3, complex_taps=True) if cc else synth.lowpass_taps(T, D)).to(dev)
     y = torch.zeros(n_out, dtype=torch.float32 if real else torch.complex64, device=dev)
     stream = torch.cuda.Stream()
     fn = g.gsdrFirFF if real else (g.gsdrFirCC if cc else g.gsdrFirFC)
+    if i8:
+        fn = g.gsdrFirFCInt8
     if args.nco:
+        nco_fn = g.gsdrAdjustFrequencyFirFCInt8 if i8 else g.gsdrAdjustFrequencyFirFC
+
         def fn(D_, taps_, T_, x_, y_, n_, dev_, stream_):  # noqa: E306
-            g.gsdrAdjustFrequencyFirFC(2.4e6, 29520.0, 12345, D_, taps_, T_, x_, y_, n_, dev_, stream_)
+            nco_fn(2.4e6, 29520.0, 12345, D_, taps_, T_, x_, y_, n_, dev_, stream_)
     esz = 4 if real else 8
-    bytes_alg = esz * n_in + esz * n_out + 4 * T
+    bytes_alg = (2 if i8 else esz) * n_in + esz * n_out + 4 * T
     flops = (2.0 if real else (8.0 if cc else 4.0)) * T * n_out
     if args.peaks:
         lib = ctypes.CDLL(str(ROOT / "tools" / "libubench_fp32.so"))
@@ -76,10 +83,10 @@ def main():
             print(json.dumps({"peak": "fp32", "blocks_per_sm": bps, "ffma_tflops": lib.ubenchFp32Tflops(0, 0, 8000, 3, bps),
                               "ffma2_tflops": lib.ubenchFp32Tflops(1, 0, 8000, 3, bps)}), flush=True)
     ref = None
-    for v in list(range(g.num_kernel_variants())) + [-2]:
+    for v in ([-1, -2] if i8 else list(range(g.num_kernel_variants())) + [-2]):
         g.set_kernel_variant(v)
         info = g.describe_kernel(1 if real else (2 if cc else (4 if args.nco else 0)), D, T, n_out)
-        if v >= 0 and info.variant != v:
+        if not i8 and v >= 0 and info.variant != v:
             print(json.dumps({"variant": v, "skipped": "does not fit"}), flush=True)
             continue
         y.zero_()
