@@ -237,6 +237,8 @@ def main() -> None:
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     dist_on = world > 1
+    # several ranks: keep each rank's pinned host buffers on the NUMA node of its GPU (e2e is host-memory bound)
+    numa_node = gd.bind_to_gpu_numa_node(local) if dist_on else None
 
     # ---- this rank's block of the capture, resident in HBM before timing starts ----
     n_in_total = n_in_gpu * world
@@ -430,7 +432,7 @@ def main() -> None:
         e2e = {"value": n_in_total / (dt / e2e_steps) / 1e6, "unit": UNIT, "h2d_bytes_per_step": h2d,
                "d2h_bytes_per_step": d2h, "ms_per_step": dt / e2e_steps * 1e3, "steps": e2e_steps,
                "timing": "host wall clock around the blocking API call (copies + kernels + sync), max over ranks",
-               "matches_device_path": ok}
+               "matches_device_path": ok, "numa_node_rank0": numa_node}
 
     if rank != 0:
         if dist_on:

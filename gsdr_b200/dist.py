@@ -34,6 +34,29 @@ def init_from_env(backend: Optional[str] = None) -> tuple[int, int, int]:
     return rank, world, local
 
 
+def bind_to_gpu_numa_node(device_index: int) -> Optional[int]:
+    """Pins this process to the CPUs of the NUMA node the GPU hangs off, so that pinned host buffers allocated
+    afterwards are local to the GPU's PCIe root (host-buffer runs with several ranks are bound by host memory
+    placement, not by the GPUs).  Returns the node, or None when the topology cannot be read (nothing is changed)."""
+    try:
+        props = torch.cuda.get_device_properties(device_index)
+        bus = f"{props.pci_domain_id:04x}:{props.pci_bus_id:02x}:{props.pci_device_id:02x}.0"
+        node = int(open(f"/sys/bus/pci/devices/{bus}/numa_node").read().strip())
+        if node < 0:
+            return None
+        cpus: set[int] = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = cpus & os.sched_getaffinity(0)
+        if not allowed:
+            return None
+        os.sched_setaffinity(0, allowed)
+        return node
+    except Exception:
+        return None
+
+
 def time_shard(num_outputs: int, decimation: int, tap_count: int, first_sample_index: int, world: int, rank: int):
     """This rank's contiguous block of outputs of one long capture (gsdrShardPlanTime)."""
     return api.shard_plan_time(num_outputs, decimation, tap_count, first_sample_index, world, rank)
