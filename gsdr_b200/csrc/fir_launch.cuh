@@ -227,10 +227,10 @@ static cudaError_t launchCcD(int variant, const CUtensorMap& map, TmaParams& P, 
   }
 }
 
-template <int TG, int PSPLIT, int DT, int MIXW, int NWIN, int NRAW, int MINB>
+template <int TG, int PSPLIT, int DT, int MIXW, int NWIN, int NRAW, int MINB, int NPLANE = 1>
 static cudaError_t launchRealT(RealParams& P, size_t smem, int dev, int smCount, cudaStream_t stream) noexcept {
   static std::atomic<size_t> configured[64];
-  auto kernel = firTmaRealKernel<TG, PSPLIT, DT, MIXW, NWIN, NRAW, MINB>;
+  auto kernel = firTmaRealKernel<TG, PSPLIT, DT, MIXW, NWIN, NRAW, MINB, NPLANE>;
   constexpr int kThreads = TG * PSPLIT + 32 * MIXW;
   if (smem > configured[dev & 63].load(std::memory_order_acquire)) {
     cudaError_t st = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -262,6 +262,33 @@ static cudaError_t launchRealD(int variant, RealParams& P, size_t smem, int dev,
 #define X(id, tg, ps, mw, nw, nr, mb) \
   case id: return launchRealT<tg, ps, DT, mw, nw, nr, mb>(P, smem, dev, smCount, stream);
     GSDR_REAL_VARIANTS(X)
+#undef X
+    default: return cudaErrorInvalidValue;
+  }
+}
+
+// Real input x complex taps (gsdrFirCF: firTmaRealKernel with two tap planes):
+// X(id, TG, PSPLIT, MIXW, NWIN, NRAW, MINB), PSPLIT even
+#define GSDR_CF_VARIANTS(X) \
+  X(0, 64, 2, 4, 1, 3, 2)   \
+  X(1, 32, 2, 2, 2, 2, 4)   \
+  X(2, 64, 2, 4, 2, 2, 2)   \
+  X(3, 32, 4, 4, 1, 3, 2)
+
+static constexpr RealVariant kCfVariants[] = {
+#define X(id, tg, ps, mw, nw, nr, mb) {tg, ps, mw, nw, nr, mb},
+    GSDR_CF_VARIANTS(X)
+#undef X
+};
+static constexpr int kNumCfVariants = (int)(sizeof(kCfVariants) / sizeof(kCfVariants[0]));
+
+template <int DT>
+static cudaError_t launchCfD(int variant, RealParams& P, size_t smem, int dev, int smCount,
+                             cudaStream_t stream) noexcept {
+  switch (variant) {
+#define X(id, tg, ps, mw, nw, nr, mb) \
+  case id: return launchRealT<tg, ps, DT, mw, nw, nr, mb, 2>(P, smem, dev, smCount, stream);
+    GSDR_CF_VARIANTS(X)
 #undef X
     default: return cudaErrorInvalidValue;
   }
@@ -332,6 +359,12 @@ GSDR_DECLARE_TMA_DT(0) GSDR_DECLARE_TMA_DT(4) GSDR_DECLARE_TMA_DT(8) GSDR_DECLAR
 GSDR_DECLARE_SPEC_DT(0) GSDR_DECLARE_SPEC_DT(8) GSDR_DECLARE_SPEC_DT(10) GSDR_DECLARE_SPEC_DT(32)
 GSDR_DECLARE_CC_DT(0) GSDR_DECLARE_CC_DT(8)
 GSDR_DECLARE_REAL_DT(0) GSDR_DECLARE_REAL_DT(2) GSDR_DECLARE_REAL_DT(10)
+#define GSDR_DECLARE_CF_DT(DT) cudaError_t launchCfDt##DT(int variant, GSDR_REAL_ARGS) noexcept;
+GSDR_DECLARE_CF_DT(0) GSDR_DECLARE_CF_DT(2) GSDR_DECLARE_CF_DT(10)
+#define GSDR_DEFINE_CF_DT(DT)                                                  \
+  cudaError_t launchCfDt##DT(int variant, GSDR_REAL_ARGS) noexcept {           \
+    return launchCfD<DT>(variant, P, smem, dev, smCount, stream);              \
+  }
 #define GSDR_INT8_ARGS Int8Params &P, size_t smem, int dev, int smCount, cudaStream_t stream
 #define GSDR_DECLARE_INT8_DT(DT) cudaError_t launchInt8Dt##DT(bool nco, int variant, GSDR_INT8_ARGS) noexcept;
 GSDR_DECLARE_INT8_DT(0) GSDR_DECLARE_INT8_DT(8) GSDR_DECLARE_INT8_DT(10)

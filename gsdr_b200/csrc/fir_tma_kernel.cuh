@@ -773,9 +773,14 @@ __device__ __forceinline__ void bulkLoad1d(void* dst, const void* src, unsigned 
 
 constexpr unsigned kRealPlanePad = 16;
 
-template <int TG, int PSPLIT, int DT, int MIXW, int NWIN, int NRAW, int MINB>
+// NPLANE = 2: complex taps (gsdrFirCF; ref: src/fir.cu:26-71 for <float, cuComplex, cuComplex>).  As in
+// firTmaCcKernel the branch groups split into a real and an imaginary tap plane over the same window (PSPLIT even);
+// group 0 collects the real plane into (re[2n], re[2n+1]) and the imaginary plane into (im[2n], im[2n+1]) and stores
+// the two complex outputs (re[2n], im[2n], re[2n+1], im[2n+1]) with one 16-byte store.
+template <int TG, int PSPLIT, int DT, int MIXW, int NWIN, int NRAW, int MINB, int NPLANE = 1>
 __global__ void __launch_bounds__(TG* PSPLIT + 32 * MIXW, MINB) firTmaRealKernel(const RealParams P) {
   static_assert(NWIN == 1 || NWIN == 2, "one or two window buffers");
+  static_assert(NPLANE == 1 || (NPLANE == 2 && PSPLIT % 2 == 0), "two tap planes need an even number of groups");
   static_assert(NRAW >= 2 && NRAW <= 4, "raw ring of 2..4 buffers (NRAW-1 bulk copies in flight per CTA)");
   constexpr unsigned NTF = TG * PSPLIT;  // filter threads
   constexpr unsigned NTM = 32 * MIXW;    // producer threads
@@ -793,7 +798,8 @@ __global__ void __launch_bounds__(TG* PSPLIT + 32 * MIXW, MINB) firTmaRealKernel
   unsigned char* bufBase = smemRaw;
   float4* scratch = reinterpret_cast<float4*>(bufBase + NWIN * bufBytes);
   float* hs = reinterpret_cast<float*>(scratch + 2u * (PSPLIT - 1) * (kTmaR / 2) * TG);
-  float* raw = hs + (size_t)D * P.Jpad + 32u;  // NRAW x rawFloats
+  const unsigned tapPlaneFloats = D * P.Jpad + 32u;
+  float* raw = hs + (size_t)NPLANE * tapPlaneFloats;  // NRAW x rawFloats
 
   const unsigned tid = threadIdx.x;
   const unsigned rowsStaged = BOUT + P.Jpad;
@@ -809,13 +815,15 @@ __global__ void __launch_bounds__(TG* PSPLIT + 32 * MIXW, MINB) firTmaRealKernel
   unsigned tile = blockIdx.x - chan * P.tilesPerChannel;
   // taps -> hs2[pp][j] = (h[j*D + 2pp], h[j*D + 2pp + 1]) by threads [0, nthreads)
   auto loadTaps = [&](unsigned c, unsigned nthreads) {
-    const float* h = P.h + (size_t)c * P.hStride;
+    const float* h = P.h + (size_t)NPLANE * c * P.hStride;  // NPLANE = 2: interleaved (re, im)
     const unsigned nh = D * P.Jpad;
-    for (unsigned i = tid; i < nh + 32u; i += nthreads) {
-      const unsigned pp = i / (2u * P.Jpad);
-      const unsigned rem = i - pp * 2u * P.Jpad;
+    for (unsigned i = tid; i < NPLANE * tapPlaneFloats; i += nthreads) {
+      const unsigned pl = (NPLANE == 2 && i >= tapPlaneFloats) ? 1u : 0u;
+      const unsigned q = i - pl * tapPlaneFloats;
+      const unsigned pp = q / (2u * P.Jpad);
+      const unsigned rem = q - pp * 2u * P.Jpad;
       const unsigned ti = (rem >> 1) * D + 2u * pp + (rem & 1u);
-      hs[i] = (i < nh && ti < P.T) ? __ldg(h + ti) : 0.0f;
+      hs[i] = (q < nh && ti < P.T) ? __ldg(h + NPLANE * ti + pl) : 0.0f;
     }
   };
   if (chan < P.numChannels) loadTaps(chan, NTF + NTM);
@@ -929,8 +937,12 @@ __global__ void __launch_bounds__(TG* PSPLIT + 32 * MIXW, MINB) firTmaRealKernel
   const unsigned grp = tid / TG;
   const unsigned t = tid - grp * TG;
   const unsigned numPairs = D >> 1;
-  const unsigned ppBegin = (grp * numPairs) / PSPLIT;
-  const unsigned ppEnd = ((grp + 1) * numPairs) / PSPLIT;
+  constexpr unsigned NSUB = PSPLIT / NPLANE;  // groups per tap plane: they split the branch pairs
+  const unsigned plane = (NPLANE == 2) ? (grp & 1u) : 0u;
+  const unsigned sub = (NPLANE == 2) ? (grp >> 1) : grp;
+  const unsigned ppBegin = (sub * numPairs) / NSUB;
+  const unsigned ppEnd = ((sub + 1) * numPairs) / NSUB;
+  const float* hsPlane = hs + plane * tapPlaneFloats;
   const unsigned long long pairsWhole = P.nOutReal >> 1;  // output pairs with both halves inside the output
   unsigned tapsChan = chan;
   for (unsigned k = 0; chan < P.numChannels; k++, advance(chan, tile)) {
@@ -950,9 +962,9 @@ __global__ void __launch_bounds__(TG* PSPLIT + 32 * MIXW, MINB) firTmaRealKernel
     for (int r = 0; r < kTmaR; r++) acc[r] = make_float2(0.0f, 0.0f);
     if (ppBegin < ppEnd) {
       if (P.Jpad == 8u) {
-        firComputePairsShort<DT>(acc, buf, hs, t, ppBegin, ppEnd, planeBytes, P);
+        firComputePairsShort<DT>(acc, buf, hsPlane, t, ppBegin, ppEnd, planeBytes, P);
       } else {
-        firComputePairs<DT>(acc, buf, hs, t, ppBegin, ppEnd, P.Jpad, planeBytes, P);
+        firComputePairs<DT>(acc, buf, hsPlane, t, ppBegin, ppEnd, P.Jpad, planeBytes, P);
       }
     }
     mbarArrive(&emptyBar[b]);  // this thread has no more reads of the window
@@ -969,6 +981,7 @@ __global__ void __launch_bounds__(TG* PSPLIT + 32 * MIXW, MINB) firTmaRealKernel
       if (grp == 0) {
 #pragma unroll
         for (int g = 1; g < PSPLIT; g++) {
+          if (NPLANE == 2 && (g & 1)) continue;  // imaginary-plane groups are collected below
 #pragma unroll
           for (int q = 0; q < kTmaR / 2; q++) {
             const float4 v = red[((g - 1) * (kTmaR / 2) + q) * TG + t];
@@ -979,6 +992,42 @@ __global__ void __launch_bounds__(TG* PSPLIT + 32 * MIXW, MINB) firTmaRealKernel
           }
         }
       }
+    }
+    if (NPLANE == 2) {
+      if (grp == 0) {
+        // imaginary plane: (im[2n], im[2n+1]) per output pair, summed over that plane's groups in a fixed order
+        const float4* red = scratch + (size_t)(k & 1u) * (PSPLIT - 1) * (kTmaR / 2) * TG;
+        float2 im[kTmaR];
+#pragma unroll
+        for (int r = 0; r < kTmaR; r++) im[r] = make_float2(0.0f, 0.0f);
+#pragma unroll
+        for (int g = 1; g < PSPLIT; g += 2) {
+#pragma unroll
+          for (int q = 0; q < kTmaR / 2; q++) {
+            const float4 v = red[((g - 1) * (kTmaR / 2) + q) * TG + t];
+            im[2 * q].x += v.x;
+            im[2 * q].y += v.y;
+            im[2 * q + 1].x += v.z;
+            im[2 * q + 1].y += v.w;
+          }
+        }
+        const unsigned long long ob = o0 + (unsigned long long)t * kTmaR;  // first output pair of this thread
+        float2* y = P.y + (size_t)chan * P.yStride;
+        if (P.y16 && ob + kTmaR <= pairsWhole) {
+#pragma unroll
+          for (int r = 0; r < kTmaR; r++) {
+            *reinterpret_cast<float4*>(y + 2 * (ob + r)) = make_float4(acc[r].x, im[r].x, acc[r].y, im[r].y);
+          }
+        } else {
+#pragma unroll
+          for (int r = 0; r < kTmaR; r++) {
+            const unsigned long long o = 2 * (ob + r);
+            if (o < P.nOutReal) y[o] = make_float2(acc[r].x, im[r].x);
+            if (o + 1 < P.nOutReal) y[o + 1] = make_float2(acc[r].y, im[r].y);
+          }
+        }
+      }
+      continue;
     }
     if (grp == 0) {
       const unsigned long long ob = o0 + (unsigned long long)t * kTmaR;  // first output pair of this thread

@@ -497,9 +497,10 @@ struct RealGeom {
 
 static bool realStaticDecimation(size_t D2) noexcept { return D2 == 2 || D2 == 10; }
 
-static bool realGeometry(const RealVariant& v, size_t Dreal, size_t T, RealGeom* g) noexcept {
+// nplane: 1 = real taps (FF), 2 = complex taps (CF: the groups split into two tap planes)
+static bool realGeometry(const RealVariant& v, size_t Dreal, size_t T, RealGeom* g, int nplane = 1) noexcept {
   const size_t D = 2 * Dreal;  // decimation of the output-pair stream
-  if (!tmaSupportedDecimation(D) || Dreal < (size_t)v.psplit) return false;
+  if (!tmaSupportedDecimation(D) || Dreal < (size_t)(v.psplit / nplane) || v.psplit % nplane != 0) return false;
   const size_t J = (T + D - 1) / D;
   const size_t Jpad = J <= 8 ? 8 : (J + 15) / 16 * 16;
   const size_t G = tmaSegBytes((unsigned)D);
@@ -518,7 +519,7 @@ static bool realGeometry(const RealVariant& v, size_t Dreal, size_t T, RealGeom*
   g->planeBytes = (unsigned)(mhp * G + kRealPlanePad);
   g->rawFloats = (unsigned)rawFloats;
   g->smemBytes = (size_t)v.nwin * (8 * D / G) * 8 * (size_t)g->planeBytes + 2 * (size_t)(v.psplit - 1) * v.tg * 64 +
-                 (D * Jpad + 32) * 4 + (size_t)v.nraw * rawFloats * 4;
+                 (size_t)nplane * (D * Jpad + 32) * 4 + (size_t)v.nraw * rawFloats * 4;
   return true;
 }
 
@@ -556,9 +557,41 @@ static int chooseRealVariant(const FirCall& c, int maxSmem, RealGeom* geom) noex
   return -1;
 }
 
+static int firstCfVariantId() noexcept { return firstCcVariantId() + kNumCcVariants; }
+
+// Returns the real-input x complex-taps variant for this call, or -1 when the call does not qualify.
+static int chooseCfVariant(const FirCall& c, int maxSmem, RealGeom* geom) noexcept {
+  if (c.type != kFirCF || c.nco != kNcoNone) return -1;
+  if (!tmaSupportedDecimation(2 * c.decimation)) return -1;
+  if ((uintptr_t)c.input % 16 != 0) return -1;
+  if (c.numChannels > 1 && (c.inputStride % 4) != 0) return -1;
+  if (c.numChannels > 0x7fffffffull) return -1;
+  auto fits = [&](int id, RealGeom* g) {
+    return id >= 0 && id < kNumCfVariants && realGeometry(kCfVariants[id], c.decimation, c.tapCount, g, 2) &&
+           g->smemBytes <= (size_t)maxSmem;
+  };
+  const int forced = gForcedVariant.load(std::memory_order_relaxed);
+  if (forced >= firstCfVariantId()) return fits(forced - firstCfVariantId(), geom) ? forced - firstCfVariantId() : -1;
+  if (forced != -1) return -1;
+  // tools/sweep.py --kind cf: 63 complex taps, D = 5, 2^27 samples: id 2 0.321 ms, id 3 0.349, id 0 0.353, id 1 0.381
+  // (direct kernel 0.484, reference 0.691); D = 1, 2^26 samples: id 1 0.486 ms, id 2 0.504, id 0 0.524 (direct 1.08)
+  static const int orderOnePair[] = {1, 2, 0, 3};
+  static const int orderMore[] = {2, 3, 0, 1};
+  const int* order = c.decimation == 1 ? orderOnePair : orderMore;
+  for (int k = 0; k < 4; k++) {
+    RealGeom g;
+    if (fits(order[k], &g)) {
+      *geom = g;
+      return order[k];
+    }
+  }
+  return -1;
+}
+
+// cfVariant >= 0: complex taps (gsdrFirCF) — `variant` is then ignored
 static cudaError_t launchReal(const FirCall& c, int variant, const RealGeom& geom, int dev, int smCount,
-                              cudaStream_t stream) noexcept {
-  const RealVariant& v = kRealVariants[variant];
+                              cudaStream_t stream, int cfVariant = -1) noexcept {
+  const RealVariant& v = cfVariant >= 0 ? kCfVariants[cfVariant] : kRealVariants[variant];
   const size_t bout = (size_t)kTmaR * v.tg;                      // output pairs per tile
   const unsigned long long pairs = (c.numOutputs + 1) / 2;
   const unsigned long long tiles = (pairs + bout - 1) / bout;
@@ -590,6 +623,12 @@ static cudaError_t launchReal(const FirCall& c, int variant, const RealGeom& geo
   P.rawFloats = geom.rawFloats;
   P.y16 = ((uintptr_t)c.output % 16 == 0 && (c.numChannels == 1 || (c.outputStride * 4) % 16 == 0)) ? 1u : 0u;
   P.dbg = (unsigned)gDebugFlags.load(std::memory_order_relaxed);
+  if (cfVariant >= 0) {
+    P.y16 = ((uintptr_t)c.output % 16 == 0 && (c.numChannels == 1 || (c.outputStride * 8) % 16 == 0)) ? 1u : 0u;
+    if (geom.staticD && D == 2) return launchCfDt2(cfVariant, P, geom.smemBytes, dev, smCount, stream);
+    if (geom.staticD && D == 10) return launchCfDt10(cfVariant, P, geom.smemBytes, dev, smCount, stream);
+    return launchCfDt0(cfVariant, P, geom.smemBytes, dev, smCount, stream);
+  }
   if (geom.staticD) {
     switch (D) {
       case 2: return launchRealDt2(variant, P, geom.smemBytes, dev, smCount, stream);
@@ -677,6 +716,8 @@ cudaError_t enqueueFir(const FirCall& c, cudaStream_t stream) noexcept {
     if (rv >= 0) return launchReal(c, rv, rg, dev, info->smCount, stream);
     const int cv = chooseCcVariant(c, info->maxSmemOptin, &tg);
     if (cv >= 0) return launchTma(c, -1, tg, dev, info->smCount, stream, cv);
+    const int fv = chooseCfVariant(c, info->maxSmemOptin, &rg);
+    if (fv >= 0) return launchReal(c, -1, rg, dev, info->smCount, stream, fv);
   }
   const bool polyType = (c.type == kFirFC || c.type == kFirFF);
   PolyGeom geom{};
@@ -952,13 +993,13 @@ GSDR_C_LINKAGE cudaError_t gsdrAdjustFrequencyFirFCInt8(float sampleRate, float 
 // ---- tuning / introspection hooks of <gsdr/b200.h> -------------------------------------------------------
 
 GSDR_C_LINKAGE int gsdrB200SetKernelVariant(int variant) GSDR_NO_EXCEPT {
-  if (variant < -2 || variant >= firstCcVariantId() + kNumCcVariants) return -1;
+  if (variant < -2 || variant >= firstCfVariantId() + kNumCfVariants) return -1;
   gForcedVariant.store(variant, std::memory_order_relaxed);
   return 0;
 }
 
 GSDR_C_LINKAGE int gsdrB200NumKernelVariants(void) GSDR_NO_EXCEPT {
-  return firstCcVariantId() + kNumCcVariants;
+  return firstCfVariantId() + kNumCfVariants;
 }
 GSDR_C_LINKAGE int gsdrB200NumPolyphaseVariants(void) GSDR_NO_EXCEPT { return kNumVariants; }
 
@@ -1022,6 +1063,28 @@ GSDR_C_LINKAGE int gsdrB200DescribeKernel(int firType, size_t decimation, size_t
       info->windowBuffers = vs.nbuf;
       info->outputsPerBlock = bout;
       info->sharedBytesPerBlock = cg.smemBytes;
+      info->numBlocks = (numOutputs + bout - 1) / bout;
+      return 0;
+    }
+  }
+  if (firType == kFirCF) {
+    FirCall probe;
+    probe.type = kFirCF;
+    probe.decimation = decimation;
+    probe.tapCount = tapCount;
+    probe.numOutputs = numOutputs;
+    RealGeom fg{};
+    const int fv = chooseCfVariant(probe, di->maxSmemOptin, &fg);
+    if (fv >= 0) {
+      const RealVariant& vs = kCfVariants[fv];
+      const size_t bout = 2 * (size_t)kTmaR * vs.tg;
+      info->variant = firstCfVariantId() + fv;
+      info->outputsPerThread = 2 * kTmaR;
+      info->threadsPerBlock = vs.threads();
+      info->phaseGroups = vs.psplit;
+      info->windowBuffers = vs.nwin;
+      info->outputsPerBlock = bout;
+      info->sharedBytesPerBlock = fg.smemBytes;
       info->numBlocks = (numOutputs + bout - 1) / bout;
       return 0;
     }

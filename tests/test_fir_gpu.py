@@ -83,8 +83,8 @@ def test_polyphase_against_oracle(kind, D, T, n_in, cuda_device):
         assert np.abs(y.astype(truth.dtype) - truth).max() <= _tol(taps, x)
 
 
-# polyphase (cp.async) | TMA-fed | warp-specialised fused NCO | real-input | complex-tap variants
-N_POLY, N_TMA, N_SPEC, N_REAL, N_ALL = 12, 24, 30, 40, 44
+# polyphase (cp.async) | TMA-fed | warp-specialised fused NCO | real-input | complex-tap | real x complex-tap variants
+N_POLY, N_TMA, N_SPEC, N_REAL, N_CC, N_ALL = 12, 24, 30, 40, 44, 48
 
 
 @pytest.mark.parametrize("variant", [-2] + list(range(N_ALL)))
@@ -142,7 +142,7 @@ def test_real_input_kernel(variant, D, T, n_out, cuda_device):
     assert dy2[1:].cpu().numpy().tobytes() == y[:n_out].tobytes()
 
 
-@pytest.mark.parametrize("variant", [-1] + list(range(N_REAL, N_ALL)))
+@pytest.mark.parametrize("variant", [-1] + list(range(N_REAL, N_CC)))
 @pytest.mark.parametrize("D,T,n_out", [(8, 255, 40_001), (2, 33, 10_000), (4, 127, 30_000), (10, 100, 9_999),
                                        (16, 500, 7_000), (32, 1023, 5_000), (6, 7, 3_000)])
 def test_complex_tap_kernel(variant, D, T, n_out, cuda_device):
@@ -154,10 +154,36 @@ def test_complex_tap_kernel(variant, D, T, n_out, cuda_device):
     info = g.describe_kernel(2, D, T, n_out)
     if variant >= 0 and info.variant == -1:
         pytest.skip("variant does not fit this shape")
-    assert info.variant >= N_REAL and (variant < 0 or info.variant == variant)
+    assert N_REAL <= info.variant < N_CC and (variant < 0 or info.variant == variant)
     y = _run("cc", D, taps, x, n_out, cuda_device)
     want = oracle.fir("cc", D, taps, x, n_out, threads=8)
     assert np.abs(y - want).max() <= _tol(taps, x)
+
+
+@pytest.mark.parametrize("variant", [-1] + list(range(N_CC, N_ALL)))
+@pytest.mark.parametrize("D,T,n_out", [(1, 63, 50_001), (5, 63, 30_001), (2, 100, 20_000), (4, 127, 9_999),
+                                       (8, 255, 8_000), (3, 7, 5_000), (16, 600, 3_001)])
+def test_real_input_complex_tap_kernel(variant, D, T, n_out, cuda_device):
+    """gsdrFirCF: the output-pair kernel of gsdrFirFF with a real and an imaginary tap plane over the same window."""
+    taps = synth.random_taps(T, 29 + D, complex_taps=True)
+    x = synth.tone_plus_noise(0, (n_out - 1) * D + T, seed=130 + D, real=True)
+    g.set_kernel_variant(variant)
+    info = g.describe_kernel(3, D, T, n_out)
+    if variant >= 0 and info.variant == -1:
+        pytest.skip("variant does not fit this shape")
+    assert N_CC <= info.variant < N_ALL and (variant < 0 or info.variant == variant)
+    dt, dx = torch.from_numpy(taps).to(cuda_device), torch.from_numpy(x).to(cuda_device)
+    dy = torch.full((n_out + 4,), 7.0, dtype=torch.complex64, device=cuda_device)
+    g.gsdrFirCF(D, dt, T, dx, dy, n_out, 0, None)
+    torch.cuda.synchronize()
+    y = dy.cpu().numpy()
+    assert (y[n_out:] == 7.0).all(), "wrote past the last output"
+    want = oracle.fir("cf", D, taps, x, n_out, threads=8)
+    assert np.abs(y[:n_out] - want).max() <= _tol(taps, x)
+    dy2 = torch.zeros(n_out + 1, dtype=torch.complex64, device=cuda_device)
+    g.gsdrFirCF(D, dt, T, dx, dy2[1:], n_out, 0, None)  # 8-byte aligned output: scalar stores
+    torch.cuda.synchronize()
+    assert dy2[1:].cpu().numpy().tobytes() == y[:n_out].tobytes()
 
 
 def test_complex_taps_batched_and_unaligned(cuda_device):

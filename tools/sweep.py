@@ -48,17 +48,17 @@ def main():
     dev = torch.device("cuda:0")
     torch.cuda.set_device(dev)
     D, T, n_in = args.D, args.T, 1 << args.log2n
-    real = args.kind == "ff"
+    real = args.kind in ("ff", "cf")  # real input
     n_out = g.fir_num_outputs(n_in, T, D)
     x = synth.tone_plus_noise(0, n_in, seed=1, device=dev, real=real)
     i8 = args.kind == "i8"
     if i8:  # int8 IQ input: the same signal quantised to 8 bits, 2 bytes per sample
         x = torch.view_as_real(x).mul(127.0).round().clamp(-127, 127).to(torch.int8).reshape(-1).contiguous()
-    cc = args.kind == "cc"
+    cc = args.kind in ("cc", "cf")
     taps = torch.from_numpy(synth.random_taps(T, 3, complex_taps=True) if cc else synth.lowpass_taps(T, D)).to(dev)
-    y = torch.zeros(n_out, dtype=torch.float32 if real else torch.complex64, device=dev)
+    y = torch.zeros(n_out, dtype=torch.float32 if args.kind == "ff" else torch.complex64, device=dev)
     stream = torch.cuda.Stream()
-    fn = g.gsdrFirFF if real else (g.gsdrFirCC if cc else g.gsdrFirFC)
+    fn = g.gsdrFirCF if args.kind == "cf" else (g.gsdrFirFF if real else (g.gsdrFirCC if cc else g.gsdrFirFC))
     if i8:
         fn = g.gsdrFirFCInt8
     if args.nco:
@@ -67,8 +67,8 @@ def main():
         def fn(D_, taps_, T_, x_, y_, n_, dev_, stream_):  # noqa: E306
             nco_fn(2.4e6, 29520.0, 12345, D_, taps_, T_, x_, y_, n_, dev_, stream_)
     esz = 4 if real else 8
-    bytes_alg = (2 if i8 else esz) * n_in + esz * n_out + 4 * T
-    flops = (2.0 if real else (8.0 if cc else 4.0)) * T * n_out
+    bytes_alg = (2 if i8 else esz) * n_in + (4 if args.kind == "ff" else 8) * n_out + 4 * T
+    flops = (4.0 if args.kind == "cf" else (2.0 if real else (8.0 if cc else 4.0))) * T * n_out
     if args.peaks:
         lib = ctypes.CDLL(str(ROOT / "tools" / "libubench_fp32.so"))
         lib.ubenchFp32Tflops.restype = ctypes.c_double
@@ -85,7 +85,7 @@ def main():
     ref = None
     for v in ([-1, -2] if i8 else list(range(g.num_kernel_variants())) + [-2]):
         g.set_kernel_variant(v)
-        info = g.describe_kernel(1 if real else (2 if cc else (4 if args.nco else 0)), D, T, n_out)
+        info = g.describe_kernel(3 if args.kind == "cf" else (1 if real else (2 if cc else (4 if args.nco else 0))), D, T, n_out)
         if not i8 and v >= 0 and info.variant != v:
             print(json.dumps({"variant": v, "skipped": "does not fit"}), flush=True)
             continue
