@@ -314,7 +314,11 @@ static int chooseTmaVariant(const FirCall& c, int maxSmem, TmaGeom* geom) noexce
     return tmaVariantFits(id, c, maxSmem, geom) ? id : -1;
   }
   if (forced != -1) return -1;
-  if (c.nco == kNcoExact) {
+  // an odd number of branch pairs (D = 6, 10, 14) cannot be split evenly over two filter groups: the single-group,
+  // single-buffered kernel then matches (D = 10: 0.262 vs 0.263 ms) or beats (D = 6: 0.411 vs 0.478 ms, 255 taps,
+  // 2^26 samples) the warp-specialised one
+  const bool oddPairCount = c.decimation <= 16 && ((c.decimation / 2) % 2 == 1);
+  if (c.nco == kNcoExact && !oddPairCount) {
     // fused NCO: copy + mix on dedicated warps, overlapped with the FIR of the previous tile
     // (tools/sweep.py --nco: 64 x 2 filter threads + 4 mixer warps for narrow rows, 32 x 4 + 4 for wide rows)
     const int sid = kNumTmaVariants + (c.decimation > 16 ? 1 : 2);
