@@ -333,6 +333,54 @@ def test_in_stream_semantics_and_graph_capture(cuda_device):
     assert np.abs(dy.cpu().numpy() - oracle.fir("fc", D, taps, x, n_out)).max() <= _tol(taps, x)
 
 
+@pytest.mark.parametrize("kind", ["ff", "cc", "cf", "nco", "i8", "stream"])
+def test_every_family_member_is_capturable(kind, cuda_device):
+    """The same in-stream contract for the other entry points: nothing runs during capture, the replay gives the
+    result of a direct call bit for bit (including the block-streaming helper's copies and two launches)."""
+    D, T, n_out = 8, 255, 9000
+    n_in = (n_out - 1) * D + T
+    ctaps = kind in ("cc", "cf")
+    taps = synth.random_taps(T, 51, complex_taps=ctaps)
+    x = synth.tone_plus_noise(0, n_in, seed=44, real=kind in ("ff", "cf"))
+    dt, dx = torch.from_numpy(taps).to(cuda_device), torch.from_numpy(x).to(cuda_device)
+    if kind == "i8":
+        dx = torch.view_as_real(dx).mul(100.0).round().to(torch.int8).reshape(-1).contiguous()
+    out_dtype = torch.float32 if kind == "ff" else torch.complex64
+    fs, f, first = 1.0e6, 12345.0, 777
+
+    st = g.FirStream(g.FirStream.FC, D, dt, T, 0.0, 0.0, 0, 0) if kind == "stream" else None
+
+    def call(out, stream):
+        if kind == "nco":
+            g.gsdrAdjustFrequencyFirFC(fs, f, first, D, dt, T, dx, out, n_out, 0, stream)
+        elif kind == "i8":
+            g.gsdrFirFCInt8(D, dt, T, dx, out, n_out, 0, stream)
+        elif kind == "stream":
+            st.reset()
+            half = (n_in // 2) & ~1
+            a = st.push(dx[:half], half, out, stream)
+            b = st.push(dx[half:], n_in - half, out[a:], stream)
+            assert a + b == n_out
+        else:
+            {"ff": g.gsdrFirFF, "cc": g.gsdrFirCC, "cf": g.gsdrFirCF}[kind](D, dt, T, dx, out, n_out, 0, stream)
+
+    s = torch.cuda.Stream()
+    want = torch.zeros(n_out, dtype=out_dtype, device=cuda_device)
+    call(want, s)  # direct call (also warms up the shared-memory attributes)
+    s.synchronize()
+    assert float(want.abs().max()) > 0
+    got = torch.zeros(n_out, dtype=out_dtype, device=cuda_device)
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph, stream=s):
+        call(got, torch.cuda.current_stream())
+    assert (got == 0).all(), "capture must not execute"
+    graph.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(got, want)
+    if st is not None:
+        st.close()
+
+
 def test_current_device_is_preserved(cuda_device):
     before = torch.cuda.current_device()
     dx = torch.ones(300, dtype=torch.float32, device=cuda_device)
