@@ -21,18 +21,28 @@ ap.add_argument("--kind", default="fc")
 ap.add_argument("--dbg", type=int, default=0)
 a = ap.parse_args()
 dev = torch.device("cuda:0")
-real = a.kind == "ff"
+real = a.kind in ("ff", "cf")
 n_in = 1 << a.log2n
 n_out = g.fir_num_outputs(n_in, a.T, a.D)
 x = synth.tone_plus_noise(0, n_in, seed=1, device=dev, real=real)
-taps = torch.from_numpy(synth.lowpass_taps(a.T, a.D)).to(dev)
-y = torch.zeros(n_out, dtype=torch.float32 if real else torch.complex64, device=dev)
+ctaps = a.kind in ("cc", "cf")
+taps = torch.from_numpy(synth.random_taps(a.T, 3, complex_taps=True) if ctaps else synth.lowpass_taps(a.T, a.D)).to(dev)
+y = torch.zeros(n_out, dtype=torch.float32 if a.kind == "ff" else torch.complex64, device=dev)
+if a.kind == "i8":
+    x = torch.view_as_real(x).mul(127.0).round().clamp(-127, 127).to(torch.int8).reshape(-1).contiguous()
 g.set_kernel_variant(a.variant)
 from gsdr_b200._lib import lib as _l
 _l.gsdrB200SetDebugFlags(a.dbg)
 for _ in range(a.launches):
-    if a.nco:
+    if a.kind == "i8":
+        (g.gsdrAdjustFrequencyFirFCInt8(2.4e6, 29520.0, 0, a.D, taps, a.T, x, y, n_out, 0, None) if a.nco
+         else g.gsdrFirFCInt8(a.D, taps, a.T, x, y, n_out, 0, None))
+    elif a.nco:
         g.gsdrAdjustFrequencyFirFC(2.4e6, 29520.0, 0, a.D, taps, a.T, x, y, n_out, 0, None)
+    elif a.kind == "cc":
+        g.gsdrFirCC(a.D, taps, a.T, x, y, n_out, 0, None)
+    elif a.kind == "cf":
+        g.gsdrFirCF(a.D, taps, a.T, x, y, n_out, 0, None)
     elif real:
         g.gsdrFirFF(a.D, taps, a.T, x, y, n_out, 0, None)
     else:
