@@ -304,6 +304,7 @@ static bool tmaVariantFits(int id, const FirCall& c, int maxSmem, TmaGeom* geom)
 // Returns the TMA variant to use for this call, or -1 when the call does not qualify.
 static int chooseTmaVariant(const FirCall& c, int maxSmem, TmaGeom* geom) noexcept {
   if (c.type != kFirFC) return -1;
+  if (c.numOutputs >= 0xfff00000ull) return -1;  // the kernel compares output-row indices in 32 bits
   if (!tmaSupportedDecimation(c.decimation) || !encodeTiled()) return -1;
   if ((uintptr_t)c.input % 16 != 0) return -1;                       // TMA needs a 16-byte aligned base
   if (c.numChannels > 1 && (c.inputStride % 2) != 0) return -1;       // ... and 16-byte strides
@@ -379,6 +380,7 @@ static int firstCcVariantId() noexcept { return kNumVariants + kNumTmaVariants +
 // Returns the complex-tap variant for this call, or -1 when the call does not qualify.
 static int chooseCcVariant(const FirCall& c, int maxSmem, TmaGeom* geom) noexcept {
   if (c.type != kFirCC || c.nco != kNcoNone) return -1;
+  if (c.numOutputs >= 0xfff00000ull) return -1;  // the kernel compares output-row indices in 32 bits
   if (!tmaSupportedDecimation(c.decimation) || !encodeTiled()) return -1;
   if ((uintptr_t)c.input % 16 != 0) return -1;
   if (c.numChannels > 1 && (c.inputStride % 2) != 0) return -1;
