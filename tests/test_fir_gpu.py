@@ -611,3 +611,44 @@ def test_config2_full_size_properties(cuda_device):
     # the in-band tone passes with |H| ~ 1: output power ~ amp^2
     p = float((dy[64:].abs() ** 2).mean())
     assert abs(p - 0.25) < 0.02
+
+
+@pytest.mark.timeout(300)
+@pytest.mark.parametrize("kind,D,T", [("fc", 8, 255), ("ff", 5, 63), ("nco", 10, 255)])
+def test_sample_indices_beyond_2_to_31(kind, D, T, cuda_device):
+    """A capture of more than 2^31 samples (the reference narrows indices to uint32, ref: src/fir.cu:30-32,53-58):
+    windows at the start, across the 2^31 and 2^32-byte marks and at the very end are recomputed by the oracle."""
+    free, _ = torch.cuda.mem_get_info()
+    real = kind == "ff"
+    n_in = (1 << 31) + (1 << 20) + 12345 if not real else (1 << 32) + (1 << 20) + 12345
+    n_out = g.fir_num_outputs(n_in, T, D)
+    need = n_in * (4 if real else 8) + n_out * (4 if real else 8) + (1 << 30)
+    if free < need:
+        pytest.skip(f"needs {need >> 30} GiB of device memory")
+    taps = synth.random_taps(T, 61)
+    gen = torch.Generator(device=cuda_device).manual_seed(1234)
+    if real:
+        dx = torch.empty(n_in, dtype=torch.float32, device=cuda_device).uniform_(-1, 1, generator=gen)
+    else:
+        dx = torch.view_as_complex(torch.empty(n_in, 2, dtype=torch.float32, device=cuda_device).uniform_(-1, 1, generator=gen))
+    dt = torch.from_numpy(taps).to(cuda_device)
+    dy = torch.zeros(n_out, dtype=torch.float32 if real else torch.complex64, device=cuda_device)
+    fs, f, first = 2.4e6, 29520.0, 2 ** 40 + 3
+    if kind == "nco":
+        g.gsdrAdjustFrequencyFirFC(fs, f, first, D, dt, T, dx, dy, n_out, 0, None)
+    else:
+        (g.gsdrFirFF if real else g.gsdrFirFC)(D, dt, T, dx, dy, n_out, 0, None)
+    torch.cuda.synchronize()
+    elem = 4 if real else 8
+    marks = [0, ((1 << 31) // D) - 100, ((1 << 32) // elem // D) - 100, ((1 << 31) + (1 << 19)) // D, n_out - 200]
+    for o0 in marks:
+        o0 = max(0, min(o0, n_out - 200))
+        xs = dx[o0 * D:(o0 + 199) * D + T].cpu().numpy()
+        if kind == "nco":
+            want = oracle.adjust_frequency_fir_fc(oracle.NCO_EXACT, fs, f, first + o0 * D, D, taps, xs, 200, f64=True)
+        else:
+            want = oracle.fir(kind, D, taps, xs, 200, f64=True)
+        got = dy[o0:o0 + 200].cpu().numpy()
+        assert np.abs(got - want).max() <= _tol(taps, xs), f"outputs {o0}.."
+    del dx, dy
+    torch.cuda.empty_cache()
