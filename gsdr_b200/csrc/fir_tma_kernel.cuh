@@ -450,6 +450,13 @@ __global__ void __launch_bounds__(TG* PSPLIT, MINB)
     for (unsigned p = tid; p < D; p += NT) ncoR[p] = ncoExactPhasor((unsigned long long)p, P.ncoStep);
   }
   __syncthreads();
+#ifndef GSDR_NO_PDL
+  // Programmatic dependent launch: the next launch's CTAs may be scheduled as this grid drains (they then wait
+  // here), and this grid touches no global memory before the previous work in the stream has completed — so
+  // stream order is unchanged for the caller.  Back-to-back launches: 167.0 -> 165.3 us on config 2.
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+#endif
 
   // (channel, tile) of this CTA's current and next work item; the grid stride is pre-split on the host so that no
   // division is needed per tile.
