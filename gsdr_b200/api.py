@@ -215,7 +215,7 @@ def stream_plan(decimation, tapCount, totalInputs, nextStart, numInputs, align=2
 class FirStream:
     """gsdrFirStream: feed blocks of any length; the concatenated outputs equal one call over the whole input."""
 
-    FC, FF, FC_NCO = 0, 1, 4
+    FC, FF, FC_NCO, FC_INT8, FC_NCO_INT8 = 0, 1, 4, 5, 6
 
     def __init__(self, firType, decimation, taps, tapCount, sampleRate=0.0, frequencyShift=0.0, firstSampleIndex=0,
                  cudaDevice=0):

@@ -790,9 +790,9 @@ cudaError_t enqueueFir(const FirCall& c, cudaStream_t stream) noexcept {
 // ---------------------------------------------------------------------------------------------------------
 // int8 IQ input (<gsdr/conversion.h>): firTmaInt8Kernel, or the direct kernel when the call does not qualify
 // ---------------------------------------------------------------------------------------------------------
-static cudaError_t enqueueInt8(bool nco, float sampleRate, float frequencyShift, size_t firstSampleIndex,
-                               size_t decimation, const float* taps, size_t tapCount, const int8_t* input,
-                               cuComplex* output, size_t numOutputs, cudaStream_t stream) noexcept {
+cudaError_t enqueueFirInt8(bool nco, float sampleRate, float frequencyShift, size_t firstSampleIndex, size_t decimation,
+                           const float* taps, size_t tapCount, const signed char* input, float2* output,
+                           size_t numOutputs, cudaStream_t stream) noexcept {
   if (numOutputs == 0) return cudaSuccess;
   if (decimation == 0) return cudaErrorInvalidValue;
   if (tapCount == 0) return cudaMemsetAsync(output, 0, numOutputs * sizeof(cuComplex), stream);
@@ -982,7 +982,8 @@ GSDR_C_LINKAGE cudaError_t gsdrFirFCInt8(size_t decimation, const float* taps, s
                                          cudaStream_t cudaStream) GSDR_NO_EXCEPT {
   DeviceScope scope(cudaDevice);
   if (scope.status() != cudaSuccess) return scope.status();
-  return enqueueInt8(false, 1.0f, 0.0f, 0, decimation, taps, tapCount, input, output, numOutputs, cudaStream);
+  return enqueueFirInt8(false, 1.0f, 0.0f, 0, decimation, taps, tapCount, (const signed char*)input, (float2*)output,
+                        numOutputs, cudaStream);
 }
 
 GSDR_C_LINKAGE cudaError_t gsdrAdjustFrequencyFirFCInt8(float sampleRate, float frequencyShift,
@@ -992,8 +993,8 @@ GSDR_C_LINKAGE cudaError_t gsdrAdjustFrequencyFirFCInt8(float sampleRate, float 
                                                         cudaStream_t cudaStream) GSDR_NO_EXCEPT {
   DeviceScope scope(cudaDevice);
   if (scope.status() != cudaSuccess) return scope.status();
-  return enqueueInt8(true, sampleRate, frequencyShift, firstSampleIndex, decimation, taps, tapCount, input, output,
-                     numOutputs, cudaStream);
+  return enqueueFirInt8(true, sampleRate, frequencyShift, firstSampleIndex, decimation, taps, tapCount,
+                        (const signed char*)input, (float2*)output, numOutputs, cudaStream);
 }
 
 // ---- tuning / introspection hooks of <gsdr/b200.h> -------------------------------------------------------

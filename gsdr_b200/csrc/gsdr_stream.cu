@@ -17,8 +17,9 @@ struct gsdrFirStream {
   float sampleRate = 0.0f, frequencyShift = 0.0f;
   size_t firstSampleIndex = 0;
   int32_t device = 0;
-  size_t elemBytes = 8;   // input and output element size (cuComplex or float)
-  uint32_t align = 2;     // samples per 16 bytes
+  size_t elemBytes = 8;   // input element size (cuComplex, float, or 2 for int8 IQ)
+  size_t outBytes = 8;    // output element size
+  uint32_t align = 2;     // input samples per 16 bytes
   float* taps = nullptr;  // device copy
   unsigned char* buffer[2] = {nullptr, nullptr};  // carry / staging, ping-pong
   int current = 0;
@@ -72,7 +73,8 @@ GSDR_C_LINKAGE cudaError_t gsdrFirStreamCreate(gsdrFirStream** stream, int firTy
   if (!stream) return cudaErrorInvalidValue;
   *stream = nullptr;
   if (decimation == 0 || tapCount == 0 || !taps) return cudaErrorInvalidValue;
-  if (firType != GSDR_STREAM_FIR_FC && firType != GSDR_STREAM_FIR_FF && firType != GSDR_STREAM_FIR_FC_NCO) {
+  if (firType != GSDR_STREAM_FIR_FC && firType != GSDR_STREAM_FIR_FF && firType != GSDR_STREAM_FIR_FC_NCO &&
+      firType != GSDR_STREAM_FIR_FC_INT8 && firType != GSDR_STREAM_FIR_FC_NCO_INT8) {
     return cudaErrorInvalidValue;
   }
   DeviceScope scope(cudaDevice);
@@ -86,7 +88,9 @@ GSDR_C_LINKAGE cudaError_t gsdrFirStreamCreate(gsdrFirStream** stream, int firTy
   s->frequencyShift = frequencyShift;
   s->firstSampleIndex = firstSampleIndex;
   s->device = cudaDevice;
-  s->elemBytes = firType == GSDR_STREAM_FIR_FF ? 4 : 8;
+  const bool int8In = firType == GSDR_STREAM_FIR_FC_INT8 || firType == GSDR_STREAM_FIR_FC_NCO_INT8;
+  s->elemBytes = firType == GSDR_STREAM_FIR_FF ? 4 : (int8In ? 2 : 8);
+  s->outBytes = firType == GSDR_STREAM_FIR_FF ? 4 : 8;
   s->align = (uint32_t)(16 / s->elemBytes);
   // carry < tapCount; the staging span of the head outputs is below carry + (align + 1) * decimation + tapCount
   const size_t capacity = (2 * tapCount + (s->align + 2) * decimation + 8) * s->elemBytes;
@@ -126,6 +130,11 @@ GSDR_C_LINKAGE size_t gsdrFirStreamNumOutputs(const gsdrFirStream* s, size_t num
 
 static cudaError_t streamFir(const gsdrFirStream* s, const void* input, void* output, size_t numOutputs,
                              uint64_t absoluteIndex, cudaStream_t stream) noexcept {
+  if (s->firType == GSDR_STREAM_FIR_FC_INT8 || s->firType == GSDR_STREAM_FIR_FC_NCO_INT8) {
+    return enqueueFirInt8(s->firType == GSDR_STREAM_FIR_FC_NCO_INT8, s->sampleRate, s->frequencyShift,
+                          s->firstSampleIndex + (size_t)absoluteIndex, s->decimation, s->taps, s->tapCount,
+                          (const signed char*)input, (float2*)output, numOutputs, stream);
+  }
   FirCall c;
   c.type = s->firType == GSDR_STREAM_FIR_FF ? kFirFF : kFirFC;
   c.nco = s->firType == GSDR_STREAM_FIR_FC_NCO ? kNcoExact : kNcoNone;
@@ -177,7 +186,7 @@ GSDR_C_LINKAGE cudaError_t gsdrFirStreamPush(gsdrFirStream* s, const void* input
     if (st != cudaSuccess) return st;
   }
   if (p.bodyOutputs > 0) {
-    st = streamFir(s, (const unsigned char*)input + p.bodyOffset * eb, (unsigned char*)output + p.headOutputs * eb,
+    st = streamFir(s, (const unsigned char*)input + p.bodyOffset * eb, (unsigned char*)output + p.headOutputs * s->outBytes,
                    (size_t)p.bodyOutputs, s->nextStart + p.headOutputs * s->decimation, stream);
     if (st != cudaSuccess) return st;
   }

@@ -31,6 +31,11 @@ struct FirCall {
 // Enqueue on `stream` of the CURRENT device (callers switch devices). No sync, no allocation.
 cudaError_t enqueueFir(const FirCall& call, cudaStream_t stream) noexcept;
 
+// int8 IQ input (<gsdr/conversion.h>): conversion fused into the staging, optional exact NCO.  Same conventions.
+cudaError_t enqueueFirInt8(bool nco, float sampleRate, float frequencyShift, size_t firstSampleIndex, size_t decimation,
+                           const float* taps, size_t tapCount, const signed char* input, float2* output,
+                           size_t numOutputs, cudaStream_t stream) noexcept;
+
 // Saves the current device, switches to `device`, restores on destruction (ref: the SIMPLE_CUDA_FNC_START/END
 // pair at src/cuComplexOperatorOverloads.cuh:74-93).
 class DeviceScope {

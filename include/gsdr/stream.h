@@ -31,7 +31,9 @@ typedef struct gsdrFirStream gsdrFirStream;
 enum {
   GSDR_STREAM_FIR_FC = 0,     /* cuComplex input, float taps (gsdrFirFC) */
   GSDR_STREAM_FIR_FF = 1,     /* float input, float taps (gsdrFirFF) */
-  GSDR_STREAM_FIR_FC_NCO = 4  /* gsdrAdjustFrequencyFirFC: NCO mix-down fused in front of the FIR */
+  GSDR_STREAM_FIR_FC_NCO = 4, /* gsdrAdjustFrequencyFirFC: NCO mix-down fused in front of the FIR */
+  GSDR_STREAM_FIR_FC_INT8 = 5,     /* gsdrFirFCInt8: interleaved int8 I/Q input (2 bytes per sample), cuComplex output */
+  GSDR_STREAM_FIR_FC_NCO_INT8 = 6  /* gsdrAdjustFrequencyFirFCInt8 */
 };
 
 /* What one push does, as a function of the counters alone. */
@@ -50,8 +52,8 @@ typedef struct gsdrStreamPlan {
 /*
  * totalInputs: samples pushed so far; nextStart: absolute index of the first sample of the next output's window
  * (0 for a new stream); align: body windows start on a multiple of `align` samples of the block when a few extra
- * head outputs can achieve it (2 for cuComplex, 4 for float: 16-byte alignment keeps the bulk-copy kernels
- * eligible), 1 to disable.  Returns 0, or -1 on invalid arguments.
+ * head outputs can achieve it (2 for cuComplex, 4 for float, 8 for int8 I/Q: 16-byte alignment keeps the bulk-copy
+ * kernels eligible), 1 to disable.  Returns 0, or -1 on invalid arguments.
  */
 GSDR_C_LINKAGE GSDR_PUBLIC int gsdrFirStreamPlan(
     uint64_t decimation,
@@ -87,7 +89,7 @@ GSDR_C_LINKAGE GSDR_PUBLIC void gsdrFirStreamReset(gsdrFirStream* stream) GSDR_N
 GSDR_C_LINKAGE GSDR_PUBLIC size_t gsdrFirStreamNumOutputs(const gsdrFirStream* stream, size_t numInputs) GSDR_NO_EXCEPT;
 
 /*
- * input: numInputs samples (device; cuComplex or float according to firType).  output: at least
+ * input: numInputs samples (device; cuComplex, float or int8 I/Q pairs according to firType).  output: at least
  * gsdrFirStreamNumOutputs(stream, numInputs) elements.  *numOutputs (may be NULL) receives the count — known on the
  * host when the call returns; the data follows in stream order.  input must stay valid until the work enqueued
  * here has run, like every device pointer passed to the stateless entry points.

@@ -101,3 +101,45 @@ def test_reset_restarts_the_sample_count(cuda_device):
     assert st.push(dx, n, yb) == ya.numel()
     torch.cuda.synchronize()
     assert torch.equal(ya, yb)
+
+
+@pytest.mark.parametrize("nco", [False, True])
+@pytest.mark.parametrize("D,T", [(8, 255), (10, 255), (32, 1023), (5, 63)])
+def test_int8_blocks(D, T, nco, cuda_device):
+    """int8 I/Q blocks (2 bytes per sample): blocks that are multiples of 8 samples reproduce the one-shot
+    gsdrFirFCInt8 / gsdrAdjustFrequencyFirFCInt8 bits; ragged blocks stay within the tolerance."""
+    rng = random.Random(5 * D + T + int(nco))
+    taps = synth.random_taps(T, 17 + D)
+    dt = torch.from_numpy(taps).to(cuda_device)
+    ftype = g.FirStream.FC_NCO_INT8 if nco else g.FirStream.FC_INT8
+    for ragged in (False, True):
+        blocks = [rng.choice([4096, 8192, 65536, 16, 256, 8, 0, 20000]) for _ in range(20)]
+        if ragged:
+            blocks = [b + rng.choice([0, 1, 3, 5]) for b in blocks]
+        total = sum(blocks)
+        iq = np.random.default_rng(total).integers(-128, 128, size=2 * total, dtype=np.int64).astype(np.int8)
+        di = torch.from_numpy(iq).to(cuda_device)
+        n_out = g.fir_num_outputs(total, T, D)
+        ref = torch.zeros(n_out, dtype=torch.complex64, device=cuda_device)
+        if nco:
+            g.gsdrAdjustFrequencyFirFCInt8(FS, SHIFT, FIRST, D, dt, T, di, ref, n_out, 0, None)
+        else:
+            g.gsdrFirFCInt8(D, dt, T, di, ref, n_out, 0, None)
+        st = g.FirStream(ftype, D, dt, T, FS, SHIFT, FIRST, 0)
+        outs, pos = [], 0
+        for n in blocks:
+            want = st.num_outputs(n)
+            y = torch.zeros(want + 2, dtype=torch.complex64, device=cuda_device)
+            assert st.push(di[2 * pos:2 * (pos + n)] if n else None, n, y, None) == want
+            outs.append(y[:want])
+            pos += n
+        torch.cuda.synchronize()
+        got = torch.cat(outs)
+        st.close()
+        assert got.numel() == n_out
+        if ragged:
+            x = np.maximum(np.float32(-1), iq.astype(np.float32) / np.float32(127))
+            tol = 2 * _tol(taps, x)
+            assert float((got - ref).abs().max()) <= tol
+        else:
+            assert torch.equal(got, ref), f"max diff {float((got - ref).abs().max())}"
