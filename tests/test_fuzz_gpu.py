@@ -1,6 +1,7 @@
 """Seeded random shapes through the automatic kernel choice of every entry point, against the C oracle.  The point is
 the dispatch edges: tiny output counts (fewer tiles than CTAs), tapCount below the decimation, windows that end
 exactly at the input's end, odd output counts on the pair kernels, 8-byte-aligned pointers that force the fallbacks."""
+import os
 import random
 
 import numpy as np
@@ -27,7 +28,7 @@ def _case(seed):
 
 
 @pytest.mark.timeout(120)
-@pytest.mark.parametrize("seed", list(range(84)))
+@pytest.mark.parametrize("seed", list(range(int(os.environ.get("GSDR_FUZZ_CASES", "84")))))
 def test_random_shape(seed, cuda_device):
     kind, D, T, n_out, offset = _case(seed)
     fs, f, first = 1.0e6, -123456.0, 2 ** 33 + seed
