@@ -257,6 +257,74 @@ __device__ __forceinline__ void mixBarrier() {
   }
 }
 
+// Pass 2 of the exact mix for compile-time decimations.  A thread keeps ONE residue s = mh & 7 of the row groups and
+// one chunk of CH branch pairs for the whole window, so that
+//   * its rotation-table entries R[p] live in registers for the whole window (no table loads);
+//   * the swizzle XOR (a function of mh & 7 only) is a per-thread constant: the 16-byte slot of pair pp0 + j inside
+//     a row is a per-thread register, and the only per-item address arithmetic is the row pointer;
+//   * the eight lanes of a quarter warp (s = 0..7, same plane, same pair) read eight consecutive row groups, which
+//     the swizzle spreads over all bank groups, exactly like the FIR reader.
+// Per work item (CH pairs of one row): 1 LDS.64 (row anchor) + CH x (LDS.128, 4 complex multiplies, STS.128) and a
+// handful of integer instructions; the arithmetic (w = A[m] * R[p], then x * w) and hence every result bit is that
+// of the generic loop in tmaMixWindow.
+template <int NT, int DT>
+struct MixStatic {
+  static constexpr unsigned PAIRS = (DT ? DT : 2) / 2;
+  static constexpr unsigned CH = (PAIRS % 4 == 0) ? 4 : PAIRS;  // pairs per chunk
+  static constexpr unsigned CHUNKS = PAIRS / CH;
+  static constexpr unsigned G = NT / 8;  // threads per residue
+  static constexpr bool ok = DT != 0 && NT % 8 == 0 && CH <= 7 && (G % CHUNKS == 0 || CHUNKS % G == 0);
+};
+
+template <int NT, int DT>
+__device__ __forceinline__ void tmaMixRowsStatic(unsigned char* buf, unsigned mhCount, unsigned planeBytes,
+                                                 const float2* ncoA, const float2* ncoR, const TmaParams& P,
+                                                 unsigned lt) {
+  using M = MixStatic<NT, DT>;
+  constexpr unsigned CH = M::CH, CHUNKS = M::CHUNKS, G = M::G;
+  constexpr unsigned SEG = tmaSegBytes(DT ? DT : 2);
+  constexpr unsigned PAIRS_PER_SEG = SEG / 16;
+  constexpr unsigned CK_LANES = G < CHUNKS ? G : CHUNKS;
+  constexpr unsigned V_LANES = G / CK_LANES;
+  const unsigned s = lt & 7u;
+  const unsigned rest = lt >> 3;
+  const unsigned ckLane = rest % CK_LANES, vLane = rest / CK_LANES;
+  const unsigned sw = tmaSwizzle<DT>(s, P);  // depends on mh & 7 only for every compile-time decimation
+  const unsigned vTotal = 8u * ((mhCount + 7u) >> 3);
+  for (unsigned ck = ckLane; ck < CHUNKS; ck += CK_LANES) {
+    const unsigned pp0 = ck * CH;
+    const unsigned seg = pp0 / PAIRS_PER_SEG, c0 = pp0 % PAIRS_PER_SEG;
+    float2 r[2 * CH];
+    unsigned off[CH];  // byte offset of pair pp0 + j inside a row segment of this thread's rows
+#pragma unroll
+    for (unsigned j = 0; j < CH; j++) {
+      const float4 rr = *reinterpret_cast<const float4*>(ncoR + 2u * (pp0 + j));
+      r[2 * j] = make_float2(rr.x, rr.y);
+      r[2 * j + 1] = make_float2(rr.z, rr.w);
+      off[j] = ((c0 + j) ^ sw) << 4;
+    }
+    unsigned char* base = buf + seg * 8u * planeBytes + s * SEG;
+    const float2* anchors = ncoA + s;
+    for (unsigned v = vLane; v < vTotal; v += V_LANES) {
+      const unsigned ml = v & 7u, u = v >> 3;
+      if (s + 8u * u >= mhCount) continue;
+      const float2 an = anchors[ml * mhCount + 8u * u];
+      unsigned char* row = base + ml * planeBytes + u * (8u * SEG);
+      float4 x[CH];
+#pragma unroll
+      for (unsigned j = 0; j < CH; j++) x[j] = *reinterpret_cast<const float4*>(row + off[j]);
+#pragma unroll
+      for (unsigned j = 0; j < CH; j++) {
+        const float2 w0 = cmulf(an, r[2 * j]);
+        const float2 w1 = cmulf(an, r[2 * j + 1]);
+        const float2 a = cmulf(make_float2(x[j].x, x[j].y), w0);
+        const float2 c = cmulf(make_float2(x[j].z, x[j].w), w1);
+        *reinterpret_cast<float4*>(row + off[j]) = make_float4(a.x, a.y, c.x, c.y);
+      }
+    }
+  }
+}
+
 template <int MODE, int NT, int DT, int BARRIER_ID = 0>
 __device__ __forceinline__ void tmaMixWindow(unsigned char* buf, unsigned long long in0, unsigned rows,
                                              unsigned planeBytes, float2* ncoA, const float2* ncoR,
@@ -270,6 +338,10 @@ __device__ __forceinline__ void tmaMixWindow(unsigned char* buf, unsigned long l
       ncoA[(m & 7u) * mhCount + (m >> 3)] = ncoExactPhasor(P.ncoFirst + in0 + (unsigned long long)m * D, P.ncoStep);
     }
     mixBarrier<NT, BARRIER_ID>();
+    if constexpr (MixStatic<NT, DT>::ok) {
+      tmaMixRowsStatic<NT, DT>(buf, mhCount, planeBytes, ncoA, ncoR, P, lt);
+      return;
+    }
     // pass 2: work item = (chunk of up to 4 branch pairs, plane, row group); the row anchor is loaded once per item
     const unsigned pairsPerChunk = (pairsPerRow % 4u == 0u) ? 4u : 1u;  // finer items balance better for odd counts
     const unsigned chunks = pairsPerRow / pairsPerChunk;
