@@ -6,6 +6,7 @@ order and meaning as the reference's `include/gsdr/fir.h`, with torch tensors st
 """
 from .api import (  # noqa: F401
     CudaError,
+    MultiGpu,
     FirStream,
     HostPipeline,
     describe_kernel,
@@ -22,6 +23,20 @@ from .api import (  # noqa: F401
     gsdrFirFF,
     gsdrFirFFBatched,
     gsdrFmDemod,
+    gsdrFmDemodWorkspace,
+    fm_demod_workspace_bytes,
+    release_scratch,
+    fm_chain_launches,
+    has_tuning_hooks,
+    library_path,
+    set_debug_flags,
+    gsdrFirFCMultiGpuHost,
+    gsdrAdjustFrequencyFirFCMultiGpuHost,
+    gsdrFirFCChannelsMultiGpuHost,
+    shared_buffer_create,
+    shared_buffer_open,
+    shared_buffer_close,
+    shared_buffer_destroy,
     gsdrInt8ToNormFloat,
     gsdrQuadAmDemod,
     gsdrQuadFmDemod,

@@ -9,8 +9,11 @@ import ctypes as C
 import os
 from pathlib import Path
 
-# GSDR_B200_LIB: development hook (tools/exp_build.py) to load an experimental build of the same library
+# GSDR_B200_LIB: development hook to load an experimental build of the same library
 LIB_PATH = Path(os.environ.get("GSDR_B200_LIB") or Path(__file__).resolve().parent / "csrc" / "libgsdr_b200.so")
+# The tuning build (-DGSDR_B200_TUNING): same code plus gsdrB200SetKernelVariant / gsdrB200SetDebugFlags.  Loaded on
+# demand by api.set_kernel_variant / api.set_debug_flags (variant-coverage tests, tools/sweep.py) — never by default.
+TUNING_LIB_PATH = Path(__file__).resolve().parent / "csrc" / "libgsdr_b200_tuning.so"
 
 c_size_t = C.c_size_t
 c_void_p = C.c_void_p
@@ -75,6 +78,10 @@ SIGNATURES = {
     "gsdrQuadAmDemod": (cudaError_t, [c_void_p, c_void_p, c_size_t, c_int32, c_void_p]),
     "gsdrFmDemod": (cudaError_t, [c_float, c_float, c_float, c_float, C.c_uint32, c_size_t, c_void_p, c_size_t, c_void_p,
                                   c_void_p, c_size_t, c_int32, c_void_p]),
+    "gsdrFmDemodWorkspaceBytes": (c_size_t, [c_size_t]),
+    "gsdrFmDemodWorkspace": (cudaError_t, [c_float, c_float, c_float, c_float, C.c_uint32, c_size_t, c_void_p, c_size_t,
+                                           c_void_p, c_void_p, c_size_t, c_void_p, c_size_t, c_int32, c_void_p]),
+    "gsdrB200ReleaseScratch": (cudaError_t, [c_int32]),
     # include/gsdr/b200.h
     "gsdrFirNumOutputs": (c_size_t, [c_size_t, c_size_t, c_size_t]),
     "gsdrFirNumInputs": (c_size_t, [c_size_t, c_size_t, c_size_t]),
@@ -92,6 +99,25 @@ SIGNATURES = {
                                                    c_void_p, c_void_p, c_size_t]),
     "gsdrFirFCMultiGpuHost": (cudaError_t, [C.POINTER(c_void_p), C.c_int, c_size_t, c_void_p, c_size_t, c_void_p,
                                             c_void_p, c_size_t]),
+    "gsdrFirFCInt8Host": (cudaError_t, [c_void_p, c_size_t, c_void_p, c_size_t, c_void_p, c_void_p, c_size_t]),
+    "gsdrAdjustFrequencyFirFCInt8Host": (cudaError_t, [c_void_p, c_float, c_float, c_size_t, c_size_t, c_void_p,
+                                                       c_size_t, c_void_p, c_void_p, c_size_t]),
+    "gsdrAdjustFrequencyFirFCMultiGpuHost": (cudaError_t, [C.POINTER(c_void_p), C.c_int, c_float, c_float, c_size_t,
+                                                           c_size_t, c_void_p, c_size_t, c_void_p, c_void_p, c_size_t]),
+    "gsdrFirFCChannelsMultiGpuHost": (cudaError_t, [C.POINTER(c_void_p), C.c_int, c_size_t, c_void_p, c_size_t, c_void_p,
+                                                    c_size_t, c_void_p, c_size_t, c_size_t, c_size_t]),
+    "gsdrMultiGpuCreate": (cudaError_t, [C.POINTER(c_int32), C.c_int, C.POINTER(c_void_p)]),
+    "gsdrMultiGpuDestroy": (None, [c_void_p]),
+    "gsdrMultiGpuPeerOk": (C.c_int, [c_void_p, C.c_int]),
+    "gsdrFirFCMultiGpu": (cudaError_t, [c_void_p, c_float, c_float, c_size_t, c_size_t, C.POINTER(c_void_p), c_size_t,
+                                        C.POINTER(c_void_p), C.POINTER(c_void_p), c_void_p, c_size_t, C.c_int,
+                                        C.POINTER(c_float)]),
+    "gsdrMultiGpuGather": (cudaError_t, [c_void_p, c_size_t, c_size_t, C.POINTER(c_void_p), c_void_p, c_size_t,
+                                         C.POINTER(c_float)]),
+    "gsdrSharedBufferCreate": (cudaError_t, [c_size_t, c_int32, C.POINTER(c_void_p), C.c_char_p]),
+    "gsdrSharedBufferOpen": (cudaError_t, [C.c_char_p, c_int32, C.POINTER(c_void_p)]),
+    "gsdrSharedBufferClose": (cudaError_t, [c_void_p, c_int32]),
+    "gsdrSharedBufferDestroy": (cudaError_t, [c_void_p, c_int32]),
     # include/gsdr/conversion.h
     "gsdrInt8ToNormFloat": (cudaError_t, [c_void_p, c_void_p, c_size_t, c_int32, c_void_p]),
     "gsdrFirFCInt8": (cudaError_t, _FIR_ARGS),
@@ -106,24 +132,51 @@ SIGNATURES = {
     "gsdrFirStreamNumOutputs": (c_size_t, [c_void_p, c_size_t]),
     "gsdrFirStreamPush": (cudaError_t, [c_void_p, c_void_p, c_size_t, c_void_p, C.POINTER(c_size_t), c_void_p]),
     "gsdrB200DescribeKernel": (C.c_int, [C.c_int, c_size_t, c_size_t, c_size_t, c_int32, C.POINTER(KernelInfo)]),
-    "gsdrB200SetKernelVariant": (C.c_int, [C.c_int]),
     "gsdrB200NumKernelVariants": (C.c_int, []),
     "gsdrB200NumPolyphaseVariants": (C.c_int, []),
+    "gsdrB200HasTuningHooks": (C.c_int, []),
+}
+
+# exported by the tuning build only (include/gsdr/b200.h, #ifdef GSDR_B200_TUNING)
+TUNING_SIGNATURES = {
+    "gsdrB200SetKernelVariant": (C.c_int, [C.c_int]),
     "gsdrB200SetDebugFlags": (C.c_int, [C.c_int]),
 }
 
 
-def _load() -> C.CDLL:
-    if not LIB_PATH.exists():
+def _load(path: Path, tuning: bool) -> C.CDLL:
+    if not path.exists():
         raise ImportError(
-            f"{LIB_PATH} is missing: the CUDA library has not been built (run `python gsdr_b200/build.py`). "
+            f"{path} is missing: the CUDA library has not been built (run `python gsdr_b200/build.py`). "
             "gsdr_b200 has no CPU fallback.")
-    lib = C.CDLL(str(LIB_PATH))
-    for name, (res, args) in SIGNATURES.items():
+    lib = C.CDLL(str(path))
+    sigs = dict(SIGNATURES)
+    if tuning:
+        sigs.update(TUNING_SIGNATURES)
+    for name, (res, args) in sigs.items():
         fn = getattr(lib, name)  # AttributeError if the .so does not export a declared symbol
         fn.restype = res
         fn.argtypes = args
     return lib
 
 
-lib = _load()
+lib = _load(LIB_PATH, tuning=False)  # the release library: what every call goes through by default
+_tuning = None
+_active = lib
+
+
+def tuning_lib() -> C.CDLL:
+    global _tuning
+    if _tuning is None:
+        _tuning = _load(TUNING_LIB_PATH, tuning=True)
+    return _tuning
+
+
+def active() -> C.CDLL:
+    """The library API calls go through: the release build unless a test / sweep has selected the tuning build."""
+    return _active
+
+
+def use_tuning(on: bool) -> None:
+    global _active
+    _active = tuning_lib() if on else lib

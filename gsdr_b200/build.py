@@ -14,7 +14,9 @@ from pathlib import Path
 
 ROOT = Path(__file__).resolve().parent.parent
 CSRC = ROOT / "gsdr_b200" / "csrc"
-LIB = CSRC / "libgsdr_b200.so"
+LIB = CSRC / "libgsdr_b200.so"                # the product: no tuning / debug hooks
+LIB_TUNING = CSRC / "libgsdr_b200_tuning.so"  # same sources with -DGSDR_B200_TUNING (variant override, work-skipping
+#                                               measurement flags): loaded only by variant-coverage tests and tools/sweep.py
 SOURCES = [CSRC / "gsdr_fir.cu", CSRC / "gsdr_host.cu", CSRC / "gsdr_demod.cu", CSRC / "gsdr_stream.cu",
            *sorted(CSRC.glob("fir_inst_*.cu"))]  # fir_inst_*: kernel instantiations, one unit per compile-time decimation
 HEADERS = sorted(CSRC.glob("*.cuh")) + sorted(CSRC.glob("*.h")) + sorted((ROOT / "include" / "gsdr").glob("*.h"))
@@ -48,33 +50,44 @@ def _stale(target: Path, deps) -> bool:
     return any(Path(d).stat().st_mtime > t for d in deps)
 
 
-def build_library(force: bool = False, verbose: bool = False) -> Path:
-    """Every translation unit is compiled to an object by its own nvcc process (in parallel), then linked."""
-    if not force and not _stale(LIB, SOURCES + HEADERS + [Path(__file__)]):
+def build_library(force: bool = False, verbose: bool = False, tuning: bool | None = None) -> Path:
+    """Every translation unit is compiled to an object by its own nvcc process (in parallel), then linked.
+    tuning=None builds both the release and the tuning library (one pool of compile jobs)."""
+    flavours = [False, True] if tuning is None else [tuning]
+    todo = [t for t in flavours
+            if force or _stale(LIB_TUNING if t else LIB, SOURCES + HEADERS + [Path(__file__)])]
+    if not todo:
         return LIB
     from concurrent.futures import ThreadPoolExecutor
 
-    objdir = CSRC / "build"
-    objdir.mkdir(exist_ok=True)
     nvcc = _nvcc()
 
-    def compile_one(src: Path):
+    def compile_one(job):
+        src, tun = job
+        objdir = CSRC / ("build_tuning" if tun else "build")
+        objdir.mkdir(exist_ok=True)
         obj = objdir / (src.stem + ".o")
-        cmd = [nvcc, *NVCC_FLAGS, "-c", "-I", str(ROOT / "include"), "-I", str(CSRC), "-o", str(obj), str(src)]
+        cmd = [nvcc, *NVCC_FLAGS, *(["-DGSDR_B200_TUNING"] if tun else []), "-c", "-I", str(ROOT / "include"), "-I",
+               str(CSRC), "-o", str(obj), str(src)]
         res = subprocess.run(cmd, capture_output=True, text=True)
-        return obj, cmd, res
+        return tun, obj, cmd, res
 
     # biggest units first so that they do not end up alone at the tail
     order = sorted(SOURCES, key=lambda p: (0 if p.name.startswith("fir_inst_") or p.name == "gsdr_fir.cu" else 1, p.name))
-    with ThreadPoolExecutor(max_workers=max(1, min(len(order), os.cpu_count() or 1))) as pool:
-        results = list(pool.map(compile_one, order))
+    jobs = [(src, tun) for src in order for tun in todo]
+    with ThreadPoolExecutor(max_workers=max(1, min(len(jobs), os.cpu_count() or 1))) as pool:
+        results = list(pool.map(compile_one, jobs))
     log = ""
     failed = False
-    for obj, cmd, res in results:
+    for tun, obj, cmd, res in results:
         log += " ".join(cmd) + "\n" + res.stdout + res.stderr
         failed = failed or res.returncode != 0
-    if not failed:
-        cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", str(LIB), *[str(o) for o, _, _ in results]]
+    for tun in todo:
+        if failed:
+            break
+        target = LIB_TUNING if tun else LIB
+        cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", str(target),
+               *[str(o) for t, o, _, _ in results if t == tun]]
         res = subprocess.run(cmd, capture_output=True, text=True)
         log += " ".join(cmd) + "\n" + res.stdout + res.stderr
         failed = res.returncode != 0

@@ -28,6 +28,14 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+// Work-skipping measurement hooks (skip the copies / the FIR loop / the stores) exist only in the tuning build
+// (-DGSDR_B200_TUNING, libgsdr_b200_tuning.so); the release library compiles them out.
+#ifdef GSDR_B200_TUNING
+#define GSDR_DBG(P) ((P).dbg)
+#else
+#define GSDR_DBG(P) 0u
+#endif
+
 namespace gsdr_b200 {
 
 enum PolyMode : int {
@@ -266,7 +274,7 @@ __global__ void __launch_bounds__(TG* PSPLIT, MINB) firPolyKernel(const PolyPara
   const unsigned elemBytes = kReal ? 4u : 8u;
 
   auto stageTile = [&](unsigned work, float2* xs) {
-    if (P.dbg & 1u) return;
+    if (GSDR_DBG(P) & 1u) return;
     const unsigned chan = work / P.tilesPerChannel;
     const unsigned tile = work - chan * P.tilesPerChannel;
     const unsigned long long in0 = (unsigned long long)tile * kTileOut * P.D;
@@ -334,7 +342,7 @@ __global__ void __launch_bounds__(TG* PSPLIT, MINB) firPolyKernel(const PolyPara
     float2 acc[R];
 #pragma unroll
     for (int r = 0; r < R; r++) acc[r] = make_float2(0.0f, 0.0f);
-    const unsigned pStop = (P.dbg & 2u) ? pBegin : pEnd;
+    const unsigned pStop = (GSDR_DBG(P) & 2u) ? pBegin : pEnd;
     if (pBegin < pStop) {
       constexpr unsigned BLK = R + kPolyPad;  // float2 positions per block of R samples
       const float2* xrow = xs + (size_t)t * BLK + (size_t)pBegin * P.pitch;

@@ -545,7 +545,7 @@ __global__ void __launch_bounds__(TG* PSPLIT, MINB)
   // A tile is TMA-fed when every row it stages is visible to the tensor map.
   auto tileIsFast = [&](unsigned tl) -> bool { return tl * BOUT + rowsStaged <= P.tmaRows; };
   auto issueTile = [&](unsigned c, unsigned tl, unsigned b) {
-    if (P.dbg & 1u) return;
+    if (GSDR_DBG(P) & 1u) return;
     unsigned char* buf = bufBase + b * bufBytes;
     if (tileIsFast(tl)) {
       if (tid == 0) {
@@ -600,7 +600,7 @@ __global__ void __launch_bounds__(TG* PSPLIT, MINB)
     // Data-ready: every thread waits on the tile's mbarrier itself (TMA tiles), so no CTA barrier is needed; the
     // rare cp.async tiles and tap reloads are written by other threads and do need one.
     const bool fast = tileIsFast(tile);
-    if (!(P.dbg & 1u) && fast) {
+    if (!(GSDR_DBG(P) & 1u) && fast) {
       mbarWait(&fullBar[b], (phaseBits >> b) & 1u);
       phaseBits ^= 1u << b;
     }
@@ -620,7 +620,7 @@ __global__ void __launch_bounds__(TG* PSPLIT, MINB)
     float2 acc[kTmaR];
 #pragma unroll
     for (int r = 0; r < kTmaR; r++) acc[r] = make_float2(0.0f, 0.0f);
-    const unsigned ppStop = (P.dbg & 2u) ? ppBegin : ppEnd;
+    const unsigned ppStop = (GSDR_DBG(P) & 2u) ? ppBegin : ppEnd;
     if (ppBegin < ppStop) firComputePairs<DT>(acc, buf, hs, t, ppBegin, ppStop, P.Jpad, planeBytes, P);
 
     // Partial sums of the branch-pair groups go through a small double-buffered scratch area, so ONE barrier per
@@ -651,7 +651,7 @@ __global__ void __launch_bounds__(TG* PSPLIT, MINB)
       }
       const unsigned long long ob = o0 + (unsigned long long)t * kTmaR;
       float2* y = P.y + (size_t)chan * P.yStride;
-      if (P.dbg & 4u) {
+      if (GSDR_DBG(P) & 4u) {
         if (acc[0].x == 123.456f) y[0] = acc[1];  // measurement hook: no output traffic
       } else if (P.y16 && ob + kTmaR <= P.nOut) {
 #pragma unroll

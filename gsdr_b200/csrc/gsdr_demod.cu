@@ -78,29 +78,60 @@ static cudaError_t enqueueQuadFm(const cuComplex* in, float* out, float gain, si
   return cudaPeekAtLastError();
 }
 
-// Library-private stream-ordered memory pool per device for gsdrFmDemod's low-pass scratch.  Its release
-// threshold is unlimited, so the scratch of one call is reused by the next instead of going back to the driver at
-// every synchronisation (the default pool's threshold is 0, which made back-to-back calls re-allocate: 4.3 ms
-// instead of 1.5 ms per call in bench.py --workload cfg5).  The device's default pool is left untouched.
+// Library-private stream-ordered memory pool per device for gsdrFmDemod's low-pass scratch (the workspace variant
+// gsdrFmDemodWorkspace allocates nothing).  The pool keeps freed blocks so that back-to-back calls reuse them instead
+// of going back to the driver at every synchronisation (the default pool's release threshold of 0 made every call
+// re-allocate: 4.3 ms instead of 1.5 ms per call in bench.py --workload cfg5); gsdrB200ReleaseScratch() hands the
+// memory back.  The handle is cached only once the pool is fully configured.  The device's default pool is untouched.
+static std::mutex gPoolMutex;
+static cudaMemPool_t gPools[64] = {};
+
 static cudaError_t scratchPool(int dev, cudaMemPool_t* pool) noexcept {
-  static std::mutex mu;
-  static cudaMemPool_t pools[64] = {};
   if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
-  std::lock_guard<std::mutex> lock(mu);
-  if (!pools[dev]) {
+  std::lock_guard<std::mutex> lock(gPoolMutex);
+  if (!gPools[dev]) {
     cudaMemPoolProps props = {};
     props.allocType = cudaMemAllocationTypePinned;
     props.handleTypes = cudaMemHandleTypeNone;
     props.location.type = cudaMemLocationTypeDevice;
     props.location.id = dev;
-    cudaError_t st = cudaMemPoolCreate(&pools[dev], &props);
+    cudaMemPool_t fresh = nullptr;
+    cudaError_t st = cudaMemPoolCreate(&fresh, &props);
     if (st != cudaSuccess) return st;
     uint64_t threshold = UINT64_MAX;
-    st = cudaMemPoolSetAttribute(pools[dev], cudaMemPoolAttrReleaseThreshold, &threshold);
-    if (st != cudaSuccess) return st;
+    st = cudaMemPoolSetAttribute(fresh, cudaMemPoolAttrReleaseThreshold, &threshold);
+    if (st != cudaSuccess) {
+      cudaMemPoolDestroy(fresh);
+      return st;
+    }
+    gPools[dev] = fresh;
   }
-  *pool = pools[dev];
+  *pool = gPools[dev];
   return cudaSuccess;
+}
+
+static cudaError_t fmDemodStage(float rfSampleRate, float tuningFrequency, float channelFrequency,
+                                float frequencyDeviation, uint32_t decimation, size_t firstSampleIndex,
+                                const float* lowPassTaps, size_t numLowPassTaps, const cuComplex* input, float* output,
+                                size_t numOutputs, void* lowPassed, cudaStream_t stream) noexcept {
+  FirCall c;
+  c.type = kFirFC;
+  c.nco = kNcoExact;
+  c.decimation = decimation;
+  c.taps = lowPassTaps;
+  c.tapCount = numLowPassTaps;
+  c.input = input;
+  c.output = lowPassed;
+  c.numOutputs = numOutputs + 1;
+  c.sampleRate = rfSampleRate;
+  c.frequencyShift = tuningFrequency - channelFrequency;  // ref: src/fm.cu:204
+  c.firstSampleIndex = firstSampleIndex;
+  cudaError_t st = enqueueFir(c, stream);
+  if (st == cudaSuccess) {
+    const float gain = rfSampleRate / (2.0f * 3.14159265358979323846f * frequencyDeviation);  // ref: src/fm.cu:203
+    st = enqueueQuadFm((const cuComplex*)lowPassed, output, gain, numOutputs, stream);
+  }
+  return st;
 }
 
 }  // namespace gsdr_b200
@@ -143,23 +174,35 @@ GSDR_C_LINKAGE cudaError_t gsdrFmDemod(float rfSampleRate, float tuningFrequency
   if (st != cudaSuccess) return st;
   st = cudaMallocFromPoolAsync(&lowPassed, (numOutputs + 1) * sizeof(cuComplex), pool, cudaStream);
   if (st != cudaSuccess) return st;
-  FirCall c;
-  c.type = kFirFC;
-  c.nco = kNcoExact;
-  c.decimation = decimation;
-  c.taps = lowPassTaps;
-  c.tapCount = numLowPassTaps;
-  c.input = input;
-  c.output = lowPassed;
-  c.numOutputs = numOutputs + 1;
-  c.sampleRate = rfSampleRate;
-  c.frequencyShift = tuningFrequency - channelFrequency;  // ref: src/fm.cu:204
-  c.firstSampleIndex = firstSampleIndex;
-  st = enqueueFir(c, cudaStream);
-  if (st == cudaSuccess) {
-    const float gain = rfSampleRate / (2.0f * 3.14159265358979323846f * frequencyDeviation);  // ref: src/fm.cu:203
-    st = enqueueQuadFm((const cuComplex*)lowPassed, output, gain, numOutputs, cudaStream);
-  }
+  st = fmDemodStage(rfSampleRate, tuningFrequency, channelFrequency, frequencyDeviation, decimation, firstSampleIndex,
+                    lowPassTaps, numLowPassTaps, input, output, numOutputs, lowPassed, cudaStream);
   const cudaError_t fr = cudaFreeAsync(lowPassed, cudaStream);
   return st != cudaSuccess ? st : fr;
+}
+
+GSDR_C_LINKAGE size_t gsdrFmDemodWorkspaceBytes(size_t numOutputs) GSDR_NO_EXCEPT {
+  return (numOutputs + 1) * sizeof(cuComplex);
+}
+
+GSDR_C_LINKAGE cudaError_t gsdrFmDemodWorkspace(float rfSampleRate, float tuningFrequency, float channelFrequency,
+                                                float frequencyDeviation, uint32_t decimation, size_t firstSampleIndex,
+                                                const float* lowPassTaps, size_t numLowPassTaps, const cuComplex* input,
+                                                float* output, size_t numOutputs, void* workspace,
+                                                size_t workspaceBytes, int32_t cudaDevice,
+                                                cudaStream_t cudaStream) GSDR_NO_EXCEPT {
+  DeviceScope scope(cudaDevice);
+  if (scope.status() != cudaSuccess) return scope.status();
+  if (numOutputs == 0) return cudaSuccess;
+  if (decimation == 0 || !workspace || workspaceBytes < gsdrFmDemodWorkspaceBytes(numOutputs) ||
+      (uintptr_t)workspace % 16 != 0)
+    return cudaErrorInvalidValue;
+  return fmDemodStage(rfSampleRate, tuningFrequency, channelFrequency, frequencyDeviation, decimation, firstSampleIndex,
+                      lowPassTaps, numLowPassTaps, input, output, numOutputs, workspace, cudaStream);
+}
+
+GSDR_C_LINKAGE cudaError_t gsdrB200ReleaseScratch(int32_t cudaDevice) GSDR_NO_EXCEPT {
+  if (cudaDevice < 0 || cudaDevice >= 64) return cudaErrorInvalidDevice;
+  std::lock_guard<std::mutex> lock(gPoolMutex);
+  if (!gPools[cudaDevice]) return cudaSuccess;
+  return cudaMemPoolTrimTo(gPools[cudaDevice], 0);  // blocks in use by enqueued work stay; everything else goes back
 }

@@ -76,8 +76,17 @@ static constexpr PolyVariant kVariants[] = {
 };
 static constexpr int kNumVariants = (int)(sizeof(kVariants) / sizeof(kVariants[0]));
 
+// Tuning build only (-DGSDR_B200_TUNING): process-wide variant override and work-skipping measurement flags.  The
+// release library has neither the state nor the setters; forcedVariant() / debugFlags() fold to constants there.
+#ifdef GSDR_B200_TUNING
 static std::atomic<int> gDebugFlags{0};
-static std::atomic<int> gForcedVariant{-1};  // -1 auto, -2 direct kernel, >=0 variant id (test/tuning hook)
+static std::atomic<int> gForcedVariant{-1};  // -1 auto, -2 direct kernel, >=0 variant id
+static inline int forcedVariant() noexcept { return gForcedVariant.load(std::memory_order_relaxed); }
+static inline unsigned debugFlags() noexcept { return (unsigned)gDebugFlags.load(std::memory_order_relaxed); }
+#else
+static inline int forcedVariant() noexcept { return -1; }
+static inline unsigned debugFlags() noexcept { return 0u; }
+#endif
 
 struct DeviceInfo {
   std::once_flag once;
@@ -157,7 +166,7 @@ static cudaError_t launchPolyMode(int variant, PolyParams& P, size_t smem, int d
 // Automatic choice: first variant of the preference list whose shared memory fits.
 static int choosePolyVariant(size_t D, size_t T, size_t nOut, int maxSmem, PolyGeom* geom,
                              bool doubleBuffered = false) noexcept {
-  const int forced = gForcedVariant.load(std::memory_order_relaxed);
+  const int forced = forcedVariant();
   if (forced == -2) return -1;
   if (forced >= 0 && forced < kNumVariants) {
     return (polyGeometry(kVariants[forced], D, T, geom) && geom->smemBytes <= (size_t)maxSmem) ? forced : -1;
@@ -309,7 +318,7 @@ static int chooseTmaVariant(const FirCall& c, int maxSmem, TmaGeom* geom) noexce
   if ((uintptr_t)c.input % 16 != 0) return -1;                       // TMA needs a 16-byte aligned base
   if (c.numChannels > 1 && (c.inputStride % 2) != 0) return -1;       // ... and 16-byte strides
   if (c.numChannels > 0x7fffffffull) return -1;
-  const int forced = gForcedVariant.load(std::memory_order_relaxed);
+  const int forced = forcedVariant();
   if (forced >= kNumVariants) {
     const int id = forced - kNumVariants;
     return tmaVariantFits(id, c, maxSmem, geom) ? id : -1;
@@ -389,7 +398,7 @@ static int chooseCcVariant(const FirCall& c, int maxSmem, TmaGeom* geom) noexcep
     return id >= 0 && id < kNumCcVariants && ccGeometry(kCcVariants[id], c.decimation, c.tapCount, g) &&
            g->smemBytes <= (size_t)maxSmem;
   };
-  const int forced = gForcedVariant.load(std::memory_order_relaxed);
+  const int forced = forcedVariant();
   if (forced >= firstCcVariantId()) return fits(forced - firstCcVariantId(), geom) ? forced - firstCcVariantId() : -1;
   if (forced != -1) return -1;
   static const int orderNarrow[] = {0, 1, 3, 2};
@@ -448,7 +457,7 @@ static cudaError_t launchTma(const FirCall& c, int variant, const TmaGeom& geom,
   P.swzMask = geom.swzMask;
   P.tmaRows = (unsigned)(tmaRows > 0xffffffffull ? 0xffffffffull : tmaRows);
   P.y16 = ((uintptr_t)c.output % 16 == 0 && (c.numChannels == 1 || (c.outputStride * 8) % 16 == 0)) ? 1u : 0u;
-  P.dbg = (unsigned)gDebugFlags.load(std::memory_order_relaxed);
+  P.dbg = debugFlags();
   P.ncoStep = ncoPhaseStep(c.frequencyShift, c.sampleRate);
   P.ncoFirst = c.firstSampleIndex;
   P.ncoFirst32 = (uint32_t)fmodf((float)c.firstSampleIndex, c.sampleRate);  // ref: src/fm.cu:202
@@ -542,7 +551,7 @@ static int chooseRealVariant(const FirCall& c, int maxSmem, RealGeom* geom) noex
   if (c.numChannels > 1 && (c.inputStride % 4) != 0) return -1;   // ... in every channel
   if (c.numChannels > 0x7fffffffull) return -1;
   const int firstId = kNumVariants + kNumTmaVariants + kNumSpecVariants;
-  const int forced = gForcedVariant.load(std::memory_order_relaxed);
+  const int forced = forcedVariant();
   if (forced >= firstId) return realVariantFits(forced - firstId, c, maxSmem, geom) ? forced - firstId : -1;
   if (forced != -1) return -1;
   // decimation 1 (one branch pair, half the FFMA2s per tile of the complex kernel) is faster on the cp.async kernel:
@@ -576,7 +585,7 @@ static int chooseCfVariant(const FirCall& c, int maxSmem, RealGeom* geom) noexce
     return id >= 0 && id < kNumCfVariants && realGeometry(kCfVariants[id], c.decimation, c.tapCount, g, 2) &&
            g->smemBytes <= (size_t)maxSmem;
   };
-  const int forced = gForcedVariant.load(std::memory_order_relaxed);
+  const int forced = forcedVariant();
   if (forced >= firstCfVariantId()) return fits(forced - firstCfVariantId(), geom) ? forced - firstCfVariantId() : -1;
   if (forced != -1) return -1;
   // tools/sweep.py --kind cf: 63 complex taps, D = 5, 2^27 samples: id 2 0.321 ms, id 3 0.349, id 0 0.353, id 1 0.381
@@ -628,7 +637,7 @@ static cudaError_t launchReal(const FirCall& c, int variant, const RealGeom& geo
   P.swzMask = geom.swzMask;
   P.rawFloats = geom.rawFloats;
   P.y16 = ((uintptr_t)c.output % 16 == 0 && (c.numChannels == 1 || (c.outputStride * 4) % 16 == 0)) ? 1u : 0u;
-  P.dbg = (unsigned)gDebugFlags.load(std::memory_order_relaxed);
+  P.dbg = debugFlags();
   if (cfVariant >= 0) {
     P.y16 = ((uintptr_t)c.output % 16 == 0 && (c.numChannels == 1 || (c.outputStride * 8) % 16 == 0)) ? 1u : 0u;
     if (geom.staticD && D == 2) return launchCfDt2(cfVariant, P, geom.smemBytes, dev, smCount, stream);
@@ -770,7 +779,7 @@ cudaError_t enqueueFir(const FirCall& c, cudaStream_t stream) noexcept {
   P.posStep = P.dm + kPolyPad * (P.dm / v.R);
   const size_t oe = outElemBytes(c.type);
   P.y16 = ((uintptr_t)c.output % 16 == 0 && (c.numChannels == 1 || (c.outputStride * oe) % 16 == 0)) ? 1u : 0u;
-  P.dbg = (unsigned)gDebugFlags.load(std::memory_order_relaxed);
+  P.dbg = debugFlags();
   P.ncoStep = ncoPhaseStep(c.frequencyShift, c.sampleRate);
   P.ncoFirst = c.firstSampleIndex;
   P.ncoFirst32 = (uint32_t)fmodf((float)c.firstSampleIndex, c.sampleRate);  // ref: src/fm.cu:202
@@ -803,7 +812,7 @@ cudaError_t enqueueFirInt8(bool nco, float sampleRate, float frequencyShift, siz
   if (!info || info->status != cudaSuccess) return info ? info->status : cudaErrorInvalidDevice;
   const size_t D = decimation, T = tapCount;
   const unsigned long long nIn = (unsigned long long)(numOutputs - 1) * D + T;
-  const int forced = gForcedVariant.load(std::memory_order_relaxed);
+  const int forced = forcedVariant();
 
   if (forced != -2 && tmaSupportedDecimation(D) && (uintptr_t)input % 16 == 0) {
     const size_t J = (T + D - 1) / D;
@@ -999,21 +1008,26 @@ GSDR_C_LINKAGE cudaError_t gsdrAdjustFrequencyFirFCInt8(float sampleRate, float 
 
 // ---- tuning / introspection hooks of <gsdr/b200.h> -------------------------------------------------------
 
+#ifdef GSDR_B200_TUNING
 GSDR_C_LINKAGE int gsdrB200SetKernelVariant(int variant) GSDR_NO_EXCEPT {
   if (variant < -2 || variant >= firstCfVariantId() + kNumCfVariants) return -1;
   gForcedVariant.store(variant, std::memory_order_relaxed);
   return 0;
 }
 
-GSDR_C_LINKAGE int gsdrB200NumKernelVariants(void) GSDR_NO_EXCEPT {
-  return firstCfVariantId() + kNumCfVariants;
-}
-GSDR_C_LINKAGE int gsdrB200NumPolyphaseVariants(void) GSDR_NO_EXCEPT { return kNumVariants; }
-
 GSDR_C_LINKAGE int gsdrB200SetDebugFlags(int flags) GSDR_NO_EXCEPT {
   gDebugFlags.store(flags & 7, std::memory_order_relaxed);
   return 0;
 }
+GSDR_C_LINKAGE int gsdrB200HasTuningHooks(void) GSDR_NO_EXCEPT { return 1; }
+#else
+GSDR_C_LINKAGE int gsdrB200HasTuningHooks(void) GSDR_NO_EXCEPT { return 0; }
+#endif
+
+GSDR_C_LINKAGE int gsdrB200NumKernelVariants(void) GSDR_NO_EXCEPT {
+  return firstCfVariantId() + kNumCfVariants;
+}
+GSDR_C_LINKAGE int gsdrB200NumPolyphaseVariants(void) GSDR_NO_EXCEPT { return kNumVariants; }
 
 GSDR_C_LINKAGE int gsdrB200DescribeKernel(int firType, size_t decimation, size_t tapCount, size_t numOutputs,
                                           int32_t cudaDevice, gsdrB200KernelInfo* info) GSDR_NO_EXCEPT {

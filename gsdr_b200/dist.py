@@ -101,3 +101,68 @@ def gather_outputs(local: torch.Tensor, counts: List[int], dst: int = 0) -> Opti
         return None
     out = torch.cat([recv[r][: counts[r]] for r in range(world)], dim=0)
     return torch.view_as_complex(out.contiguous()) if is_complex else out
+
+
+def gather_outputs_p2p(local: torch.Tensor, counts: List[int], firsts: List[int], full: Optional[torch.Tensor],
+                       dst: int = 0) -> Optional[torch.Tensor]:
+    """Collects the ranks' output blocks on rank `dst` with grouped point-to-point operations (NCCL: ncclGroupStart,
+    one ncclSend per sender / one ncclRecv per sender on `dst`, ncclGroupEnd): every block is received straight at its
+    final offset `firsts[r]` of `full` (preallocated on `dst`, None elsewhere) — no padding, no concatenation.  The
+    rank that owns `dst` copies its own block on the device.  Works with gloo too (CPU tests)."""
+    if not dist.is_initialized() or dist.get_world_size() == 1:
+        if full is not None:
+            full[firsts[0]: firsts[0] + counts[0]].copy_(local)
+        return full
+    world, rank = dist.get_world_size(), dist.get_rank()
+    assert len(counts) == world and len(firsts) == world and local.shape[0] == counts[rank]
+    ops = []
+    if rank == dst:
+        assert full is not None
+        for r in range(world):
+            if r != dst and counts[r]:
+                ops.append(dist.P2POp(dist.irecv, full[firsts[r]: firsts[r] + counts[r]], r))
+        full[firsts[dst]: firsts[dst] + counts[dst]].copy_(local, non_blocking=True)
+    elif counts[rank]:
+        ops.append(dist.P2POp(dist.isend, local, dst))
+    if ops:
+        for w in dist.batch_isend_irecv(ops):
+            w.wait()
+    return full
+
+
+class PeerOutput:
+    """An output buffer on rank 0's GPU that every rank's kernels can store into (gsdrSharedBuffer*: cudaIpc mapping
+    over NVLink).  rank 0 creates it and broadcasts the 64-byte handle; the others open it.  `ptr` is the address
+    valid in THIS process — pass `ptr + firstOutput * 8` as `output` of gsdrFirFC to gather while computing."""
+
+    def __init__(self, nbytes: int, rank: int, local_device: int, device):
+        self.rank, self.local = rank, local_device
+        self.nbytes = nbytes
+        handle = torch.zeros(64, dtype=torch.uint8, device=device)
+        if rank == 0:
+            self.ptr, raw = api.shared_buffer_create(nbytes, local_device)
+            handle.copy_(torch.frombuffer(bytearray(raw), dtype=torch.uint8))
+        if dist.is_initialized() and dist.get_world_size() > 1:
+            dist.broadcast(handle, src=0)
+        if rank != 0:
+            self.ptr = api.shared_buffer_open(bytes(handle.cpu().numpy().tobytes()), local_device)
+
+    def as_tensor(self, count: int) -> torch.Tensor:
+        """rank 0 only: the buffer as a complex64 tensor (copied out through a raw device-to-device memcpy)."""
+        import ctypes
+
+        out = torch.empty(count, dtype=torch.complex64, device=torch.device("cuda", self.local))
+        rt = ctypes.CDLL("libcudart.so.12")
+        rt.cudaMemcpy.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int]
+        rc = rt.cudaMemcpy(out.data_ptr(), self.ptr, count * 8, 3)  # cudaMemcpyDeviceToDevice
+        if rc:
+            raise api.CudaError(rc, "cudaMemcpy")
+        return out
+
+    def close(self) -> None:
+        if self.ptr:
+            if self.rank == 0:
+                api.shared_buffer_destroy(self.ptr, self.local)
+            else:
+                api.shared_buffer_close(self.ptr, self.local)
+            self.ptr = 0

@@ -159,6 +159,124 @@ GSDR_C_LINKAGE GSDR_PUBLIC cudaError_t gsdrFirFCMultiGpuHost(
     cuComplex* output,
     size_t numOutputs) GSDR_NO_EXCEPT;
 
+/* The same for int8 I/Q host input (2 bytes per complex sample over PCIe; <gsdr/conversion.h> semantics). */
+GSDR_C_LINKAGE GSDR_PUBLIC cudaError_t gsdrFirFCInt8Host(
+    gsdrHostPipeline* pipeline,
+    size_t decimation,
+    const float* taps,
+    size_t tapCount,
+    const int8_t* input,
+    cuComplex* output,
+    size_t numOutputs) GSDR_NO_EXCEPT;
+
+GSDR_C_LINKAGE GSDR_PUBLIC cudaError_t gsdrAdjustFrequencyFirFCInt8Host(
+    gsdrHostPipeline* pipeline,
+    float sampleRate,
+    float frequencyShift,
+    size_t firstSampleIndex,
+    size_t decimation,
+    const float* taps,
+    size_t tapCount,
+    const int8_t* input,
+    cuComplex* output,
+    size_t numOutputs) GSDR_NO_EXCEPT;
+
+/* Time-sharded fused NCO + FIR over several pipelines (the NCO index of every shard is advanced exactly). */
+GSDR_C_LINKAGE GSDR_PUBLIC cudaError_t gsdrAdjustFrequencyFirFCMultiGpuHost(
+    gsdrHostPipeline* const* pipelines,
+    int numPipelines,
+    float sampleRate,
+    float frequencyShift,
+    size_t firstSampleIndex,
+    size_t decimation,
+    const float* taps,
+    size_t tapCount,
+    const cuComplex* input,
+    cuComplex* output,
+    size_t numOutputs) GSDR_NO_EXCEPT;
+
+/*
+ * Channel-sharded: numChannels independent host-resident channels (strides in elements, one shared tap set), channel
+ * c handled by pipeline gsdrShardPlanChannels assigns it to.
+ */
+GSDR_C_LINKAGE GSDR_PUBLIC cudaError_t gsdrFirFCChannelsMultiGpuHost(
+    gsdrHostPipeline* const* pipelines,
+    int numPipelines,
+    size_t decimation,
+    const float* taps,
+    size_t tapCount,
+    const cuComplex* input,
+    size_t inputStride,
+    cuComplex* output,
+    size_t outputStride,
+    size_t numOutputs,
+    size_t numChannels) GSDR_NO_EXCEPT;
+
+/* ---- device-resident multi-GPU executor with fused gather ----------------------------------------------- */
+/*
+ * One process, several GPUs, every shard already resident in its GPU's HBM (the layout gsdrShardPlanTime
+ * describes).  One persistent host thread and one stream per device.  No collective on the compute path.
+ *
+ * Gather ("collect the decimated outputs on one GPU when the caller asks for it"): when gatherOutput is non-NULL
+ * it must be a buffer of numOutputs elements on devices[0]; peer access is enabled at creation and EVERY device's
+ * FIR kernel stores its block straight into gatherOutput + firstOutput over NVLink — compute and gather are the
+ * same kernel, nothing is staged or copied afterwards.  With gatherOutput == NULL shard g's outputs go to
+ * outputs[g] on device g, and gsdrMultiGpuGather() can collect them later (cudaMemcpyPeerAsync, one copy per
+ * shard, each to its final offset).
+ */
+typedef struct gsdrMultiGpu gsdrMultiGpu;
+
+GSDR_C_LINKAGE GSDR_PUBLIC cudaError_t gsdrMultiGpuCreate(
+    const int32_t* devices, int numDevices, gsdrMultiGpu** executor) GSDR_NO_EXCEPT;
+GSDR_C_LINKAGE GSDR_PUBLIC void gsdrMultiGpuDestroy(gsdrMultiGpu* executor) GSDR_NO_EXCEPT;
+/* 1 when devices[g] can store into devices[0]'s memory (always 1 for g == 0) */
+GSDR_C_LINKAGE GSDR_PUBLIC int gsdrMultiGpuPeerOk(const gsdrMultiGpu* executor, int g) GSDR_NO_EXCEPT;
+
+/*
+ * taps[g], inputs[g], outputs[g]: device pointers on devices[g]; inputs[g] holds shard g's block (its first element
+ * is input sample gsdrShard.firstInput of the capture).  frequencyShift == 0 && sampleRate == 0: plain gsdrFirFC;
+ * otherwise the fused exact NCO with firstSampleIndex the index of the capture's first sample.  Blocks until every
+ * device has finished (elapsedMs, when non-NULL, receives the longest per-device kernel time measured with CUDA
+ * events around `repeats` back-to-back launches, divided by repeats).
+ */
+GSDR_C_LINKAGE GSDR_PUBLIC cudaError_t gsdrFirFCMultiGpu(
+    gsdrMultiGpu* executor,
+    float sampleRate,
+    float frequencyShift,
+    size_t firstSampleIndex,
+    size_t decimation,
+    const float* const* taps,
+    size_t tapCount,
+    const cuComplex* const* inputs,
+    cuComplex* const* outputs,
+    cuComplex* gatherOutput,
+    size_t numOutputs,
+    int repeats,
+    float* elapsedMs) GSDR_NO_EXCEPT;
+
+/* Collects shard outputs (outputs[g] on devices[g], the shard plan's counts) into dst on devices[0]. */
+GSDR_C_LINKAGE GSDR_PUBLIC cudaError_t gsdrMultiGpuGather(
+    gsdrMultiGpu* executor,
+    size_t decimation,
+    size_t tapCount,
+    const cuComplex* const* outputs,
+    cuComplex* dst,
+    size_t numOutputs,
+    float* elapsedMs) GSDR_NO_EXCEPT;
+
+/* ---- shared output buffers for one-process-per-GPU runs ------------------------------------------------- */
+/*
+ * The same fused gather when every GPU is driven by its own process (torchrun): rank 0 creates the buffer and
+ * publishes the 64-byte handle; the other ranks open it and pass the mapped pointer (plus their firstOutput) as
+ * `output` of gsdrFirFC.  Thin wrappers over cudaMalloc / cudaIpcGetMemHandle / cudaIpcOpenMemHandle.
+ */
+GSDR_C_LINKAGE GSDR_PUBLIC cudaError_t gsdrSharedBufferCreate(
+    size_t bytes, int32_t cudaDevice, void** devicePointer, unsigned char handle[64]) GSDR_NO_EXCEPT;
+GSDR_C_LINKAGE GSDR_PUBLIC cudaError_t gsdrSharedBufferOpen(
+    const unsigned char handle[64], int32_t cudaDevice, void** devicePointer) GSDR_NO_EXCEPT;
+GSDR_C_LINKAGE GSDR_PUBLIC cudaError_t gsdrSharedBufferClose(void* devicePointer, int32_t cudaDevice) GSDR_NO_EXCEPT;
+GSDR_C_LINKAGE GSDR_PUBLIC cudaError_t gsdrSharedBufferDestroy(void* devicePointer, int32_t cudaDevice) GSDR_NO_EXCEPT;
+
 /* ---- kernel selection: introspection and test/tuning hook ---------------------------------------------- */
 
 typedef struct gsdrB200KernelInfo {
@@ -183,19 +301,28 @@ GSDR_C_LINKAGE GSDR_PUBLIC int gsdrB200DescribeKernel(
     int32_t cudaDevice,
     gsdrB200KernelInfo* info) GSDR_NO_EXCEPT;
 
-/*
- * Process-wide override for tests and tuning sweeps: -1 = automatic (default), -2 = always the direct kernel,
- * k >= 0 = polyphase variant k whenever it fits (else the direct kernel).  Returns 0, or -1 if out of range.
- */
-GSDR_C_LINKAGE GSDR_PUBLIC int gsdrB200SetKernelVariant(int variant) GSDR_NO_EXCEPT;
 GSDR_C_LINKAGE GSDR_PUBLIC int gsdrB200NumKernelVariants(void) GSDR_NO_EXCEPT;
 /* Variant ids [0, gsdrB200NumPolyphaseVariants()) are the cp.async-staged polyphase kernel (any decimation, FC and
- * FF); ids from there up to gsdrB200NumKernelVariants() are the TMA-fed kernel (FC, even decimation <= 16). */
+ * FF); ids from there up to gsdrB200NumKernelVariants() are the TMA-fed kernels. */
 GSDR_C_LINKAGE GSDR_PUBLIC int gsdrB200NumPolyphaseVariants(void) GSDR_NO_EXCEPT;
+/* 1 when this library is the tuning build (the two hooks below exist), 0 for the release build. */
+GSDR_C_LINKAGE GSDR_PUBLIC int gsdrB200HasTuningHooks(void) GSDR_NO_EXCEPT;
+
+#ifdef GSDR_B200_TUNING
+/*
+ * TUNING BUILD ONLY (libgsdr_b200_tuning.so, compiled with -DGSDR_B200_TUNING; used by the variant-coverage tests
+ * and tools/sweep.py).  The release library neither exports these symbols nor contains the code behind them.
+ *
+ * Process-wide override: -1 = automatic (default), -2 = always the direct kernel, k >= 0 = kernel variant k
+ * whenever it fits (else the direct kernel).  Returns 0, or -1 if out of range.
+ */
+GSDR_C_LINKAGE GSDR_PUBLIC int gsdrB200SetKernelVariant(int variant) GSDR_NO_EXCEPT;
 /*
  * Measurement hook (results are WRONG while set): bit 0 skips the global->shared window copies, bit 1 skips the
- * FIR loop.  Lets a profiler time the two halves of the kernel separately.  0 restores normal operation.
+ * FIR loop, bit 2 the output stores.  Lets a profiler time the parts of the kernel separately.  0 restores normal
+ * operation.
  */
 GSDR_C_LINKAGE GSDR_PUBLIC int gsdrB200SetDebugFlags(int flags) GSDR_NO_EXCEPT;
+#endif /* GSDR_B200_TUNING */
 
 #endif /* GSDR_B200_INCLUDE_GSDR_B200_H_ */

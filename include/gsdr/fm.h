@@ -46,4 +46,32 @@ GSDR_C_LINKAGE GSDR_PUBLIC cudaError_t gsdrFmDemod(
     int32_t cudaDevice,
     cudaStream_t cudaStream) GSDR_NO_EXCEPT;
 
+/*
+ * Additive: the same stage with CALLER-OWNED scratch, for callers that hold the reference's "the library allocates
+ * nothing" contract (ref: include/gsdr/fir.h:25-29).  workspace: device memory on cudaDevice, 16-byte aligned, at least
+ * gsdrFmDemodWorkspaceBytes(numOutputs) bytes, not read or written by anyone else until the stream has passed the call.
+ */
+GSDR_C_LINKAGE GSDR_PUBLIC size_t gsdrFmDemodWorkspaceBytes(size_t numOutputs) GSDR_NO_EXCEPT;
+GSDR_C_LINKAGE GSDR_PUBLIC cudaError_t gsdrFmDemodWorkspace(
+    float rfSampleRate,
+    float tuningFrequency,
+    float channelFrequency,
+    float frequencyDeviation,
+    uint32_t decimation,
+    size_t firstSampleIndex,
+    const float* lowPassTaps,
+    size_t numLowPassTaps,
+    const cuComplex* input,
+    float* output,
+    size_t numOutputs,
+    void* workspace,
+    size_t workspaceBytes,
+    int32_t cudaDevice,
+    cudaStream_t cudaStream) GSDR_NO_EXCEPT;
+/*
+ * Returns the memory gsdrFmDemod's private scratch pool on cudaDevice is holding to the driver (blocks still in use by
+ * enqueued work are kept).  A long-running receiver calls this after its largest block size shrinks; never required.
+ */
+GSDR_C_LINKAGE GSDR_PUBLIC cudaError_t gsdrB200ReleaseScratch(int32_t cudaDevice) GSDR_NO_EXCEPT;
+
 #endif /* GSDR_B200_INCLUDE_GSDR_FM_H_ */

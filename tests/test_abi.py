@@ -10,10 +10,13 @@ ROOT = Path(__file__).resolve().parent.parent
 INCLUDE = ROOT / "include" / "gsdr"
 
 
-def _declared_symbols():
+def _declared_symbols(tuning: bool = False):
+    """Symbols the headers declare; the block under #ifdef GSDR_B200_TUNING only for the tuning build."""
     names = set()
     for h in sorted(INCLUDE.glob("*.h")):
         text = re.sub(r"/\*.*?\*/", "", h.read_text(), flags=re.S)
+        if not tuning:
+            text = re.sub(r"#ifdef GSDR_B200_TUNING.*?#endif", "", text, flags=re.S)
         for m in re.finditer(r"GSDR_PUBLIC\s+[\w\s\*]+?\b(gsdr\w+)\s*\(", text):
             names.add(m.group(1))
     return sorted(names)
@@ -36,12 +39,46 @@ def test_library_exports_every_declared_symbol():
         assert name in _lib.SIGNATURES, f"{name} has no ctypes signature in gsdr_b200/_lib.py"
 
 
+def _exports(path):
+    out = subprocess.run(["nm", "-D", "--defined-only", str(path)], capture_output=True, text=True).stdout
+    return {line.split()[-1] for line in out.splitlines() if " T " in line and line.split()[-1].startswith("gsdr")}
+
+
 def test_no_undeclared_gsdr_exports():
     from gsdr_b200 import _lib
 
-    out = subprocess.run(["nm", "-D", "--defined-only", str(_lib.LIB_PATH)], capture_output=True, text=True).stdout
-    exported = {line.split()[-1] for line in out.splitlines() if " T " in line and line.split()[-1].startswith("gsdr")}
-    assert exported == set(_declared_symbols())
+    assert _exports(_lib.LIB_PATH) == set(_declared_symbols())
+
+
+def test_release_library_has_no_tuning_hooks_and_tuning_library_has_them():
+    """gsdrB200SetKernelVariant / gsdrB200SetDebugFlags (process-wide, work-skipping) exist only in the tuning build."""
+    from gsdr_b200 import _lib
+
+    hooks = {"gsdrB200SetKernelVariant", "gsdrB200SetDebugFlags"}
+    assert not (hooks & _exports(_lib.LIB_PATH))
+    assert _exports(_lib.TUNING_LIB_PATH) == set(_declared_symbols(tuning=True))
+    assert hooks <= _exports(_lib.TUNING_LIB_PATH)
+    assert ctypes.CDLL(str(_lib.LIB_PATH)).gsdrB200HasTuningHooks() == 0
+    assert ctypes.CDLL(str(_lib.TUNING_LIB_PATH)).gsdrB200HasTuningHooks() == 1
+
+
+def test_compiled_c_consumer_links_and_resolves_the_reference_call_shape(tmp_path):
+    """tests/abi_consumer.c is plain C written against include/gsdr/fir.h exactly as a user of the reference writes it
+    (ref: include/gsdr/fir.h:30-38); it must compile with gcc and link against libgsdr_b200.so.  Run without a GPU it
+    only checks the error path (the call must return a cudaError_t, not crash)."""
+    from gsdr_b200 import _lib
+
+    cuda_inc, cuda_lib = "/usr/local/cuda/include", "/usr/local/cuda/lib64"
+    if not Path(cuda_inc, "cuda_runtime.h").exists():
+        pytest.skip("CUDA headers not installed")
+    exe = tmp_path / "abi_consumer"
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-I", str(ROOT / "include"), "-I", cuda_inc,
+                    str(ROOT / "tests" / "abi_consumer.c"), "-o", str(exe), "-L", str(_lib.LIB_PATH.parent),
+                    "-lgsdr_b200", "-L", cuda_lib, "-lcudart", f"-Wl,-rpath,{_lib.LIB_PATH.parent}",
+                    f"-Wl,-rpath,{cuda_lib}"], check=True)
+    res = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert res.returncode in (0, 3), res.stdout + res.stderr  # 0: ran on a GPU and matched; 3: no device (error path)
+    assert "gsdrFirFC" in res.stdout
 
 
 def test_fir_signature_matches_reference_argument_order():
@@ -83,3 +120,19 @@ def test_nco_phase_step_matches_oracle():
 
     for f, fs in [(100e3, 2.4e6), (-100e3, 2.4e6), (0.0, 1e6), (1.2e6, 2.4e6), (29520.0, 2.4e6), (7.0e6, 2.4e6)]:
         assert g.nco_phase_step(f, fs) == oracle.nco_exact_phase_step(f, fs)
+
+
+@pytest.mark.gpu
+def test_compiled_c_consumer_runs_on_the_gpu(tmp_path):
+    """The same plain-C program on a device: the impulse response must come back exactly (exit code 0)."""
+    from gsdr_b200 import _lib
+
+    cuda_inc, cuda_lib = "/usr/local/cuda/include", "/usr/local/cuda/lib64"
+    exe = tmp_path / "abi_consumer"
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-I", str(ROOT / "include"), "-I", cuda_inc,
+                    str(ROOT / "tests" / "abi_consumer.c"), "-o", str(exe), "-L", str(_lib.LIB_PATH.parent),
+                    "-lgsdr_b200", "-L", cuda_lib, "-lcudart", f"-Wl,-rpath,{_lib.LIB_PATH.parent}",
+                    f"-Wl,-rpath,{cuda_lib}"], check=True)
+    res = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert res.returncode == 0, res.stdout + res.stderr
+    assert "impulse response ok" in res.stdout

@@ -35,6 +35,28 @@ def test_time_shards_partition_outputs_exactly():
                     assert nxt == n_out
 
 
+def test_pure_python_plan_equals_the_c_abi_plan():
+    """harness/plan.py (used by bench.py's reference arm, which must not map the product library) restates
+    gsdrShardPlanTime / gsdrShardPlanChannels / gsdrFirNum*: identical integers."""
+    from harness import plan
+
+    for n_out in (0, 1, 5, 1000, 8_388_577, 214_748_340, 2 ** 40 + 17):
+        for D, T in ((1, 63), (8, 255), (32, 1023), (50, 885)):
+            for S in (1, 2, 3, 8):
+                for s in range(S):
+                    a, b = g.shard_plan_time(n_out, D, T, 12345, S, s), plan.shard_plan_time(n_out, D, T, 12345, S, s)
+                    assert (a.firstOutput, a.numOutputs, a.firstInput, a.numInputs, a.firstSampleIndex) == (
+                        b.firstOutput, b.numOutputs, b.firstInput, b.numInputs, b.firstSampleIndex)
+    for C in (0, 1, 7, 1024):
+        for S in (1, 3, 8):
+            for s in range(S):
+                assert g.shard_plan_channels(C, S, s) == plan.shard_plan_channels(C, S, s)
+    for n_in in (0, 62, 63, 1 << 20, 1 << 26, (1 << 31) + 5):
+        for D, T in ((1, 63), (8, 255), (10, 255)):
+            assert g.fir_num_outputs(n_in, T, D) == plan.fir_num_outputs(n_in, T, D)
+            assert g.fir_num_inputs(n_in, T, D) == plan.fir_num_inputs(n_in, T, D)
+
+
 def test_neighbouring_time_shards_overlap_by_taps_minus_decimation():
     n_out, D, T, S = 1000, 8, 255, 4
     shards = [g.shard_plan_time(n_out, D, T, 0, S, s) for s in range(S)]
@@ -108,6 +130,12 @@ def _gloo_worker(rank: int, world: int, port: int, n_in: int, ret):
     t = gd.max_over_ranks(float(r + 1))
     assert t == float(w)
     got = gd.gather_outputs(torch.from_numpy(y_local), counts, dst=0)
+    # the unpadded point-to-point gather: every block received straight at its final offset
+    firsts = [gd.time_shard(n_out, D, T, first, w, q).firstOutput for q in range(w)]
+    full = torch.zeros(n_out, dtype=torch.complex64) if r == 0 else None
+    gd.gather_outputs_p2p(torch.from_numpy(y_local), counts, firsts, full, dst=0)
+    if r == 0:
+        ret["p2p_ok"] = bool(full.numpy().tobytes() == got.numpy().tobytes())
     if r == 0:
         x = synth.tone_plus_noise(0, n_in, seed=21)
         want = oracle.adjust_frequency_fir_fc(oracle.NCO_EXACT, fs, f, first, D, h, x, n_out)
@@ -125,3 +153,4 @@ def test_two_rank_gloo_time_shard_and_gather_is_bit_exact():
         ret = m.dict()
         mp.spawn(_gloo_worker, args=(world, port, n_in, ret), nprocs=world, join=True)
         assert ret["ok"] and ret["n"] == g.fir_num_outputs(n_in, 255, 8)
+        assert ret["p2p_ok"]

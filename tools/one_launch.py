@@ -31,8 +31,7 @@ y = torch.zeros(n_out, dtype=torch.float32 if a.kind == "ff" else torch.complex6
 if a.kind == "i8":
     x = torch.view_as_real(x).mul(127.0).round().clamp(-127, 127).to(torch.int8).reshape(-1).contiguous()
 g.set_kernel_variant(a.variant)
-from gsdr_b200._lib import lib as _l
-_l.gsdrB200SetDebugFlags(a.dbg)
+g.set_debug_flags(a.dbg)
 for _ in range(a.launches):
     if a.kind == "i8":
         (g.gsdrAdjustFrequencyFirFCInt8(2.4e6, 29520.0, 0, a.D, taps, a.T, x, y, n_out, 0, None) if a.nco

@@ -100,11 +100,10 @@ def main():
         diff = float((y - ref).abs().max())
         extra = {}
         if args.split and v >= 0:
-            from gsdr_b200._lib import lib as _l
             for name, flag in (("ms_copy_only", 2), ("ms_fir_only", 1), ("ms_fir_nostore", 5)):
-                _l.gsdrB200SetDebugFlags(flag)
+                g.set_debug_flags(flag)
                 extra[name] = timeit(lambda: fn(D, taps, T, x, y, n_out, 0, stream), stream, reps=10)[0]
-            _l.gsdrB200SetDebugFlags(0)
+            g.set_debug_flags(0)
         print(json.dumps({"variant": v, **extra, "threads": info.threadsPerBlock, "R": info.outputsPerThread,
                           "smem": info.sharedBytesPerBlock, "ctas": info.numBlocks, "ms_median": med, "ms_best": best,
                           "msamples_s": n_in / med / 1e3, "gbs": bytes_alg / med / 1e6, "tflops": flops / med / 1e9,
