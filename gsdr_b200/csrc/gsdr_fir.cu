@@ -13,6 +13,7 @@
 #include <mutex>
 
 #include "fir_launch.cuh"
+#include "fir_tc_kernel.cuh"
 
 namespace gsdr_b200 {
 
@@ -76,6 +77,8 @@ static constexpr PolyVariant kVariants[] = {
 };
 static constexpr int kNumVariants = (int)(sizeof(kVariants) / sizeof(kVariants[0]));
 
+constexpr int kForceTensorCore = -4;  // tuning hook value: tensor-core kernel wherever its shape rules allow
+constexpr int kForceNoTensorCore = -3;  // tuning hook value: automatic choice among the FFMA2 kernels only
 // Tuning build only (-DGSDR_B200_TUNING): process-wide variant override and work-skipping measurement flags.  The
 // release library has neither the state nor the setters; forcedVariant() / debugFlags() fold to constants there.
 #ifdef GSDR_B200_TUNING
@@ -87,6 +90,12 @@ static inline unsigned debugFlags() noexcept { return (unsigned)gDebugFlags.load
 static inline int forcedVariant() noexcept { return -1; }
 static inline unsigned debugFlags() noexcept { return 0u; }
 #endif
+
+// the override as the FFMA2-kernel choosers see it: the two tensor-core values mean "automatic" to them
+static inline int forcedFfmaVariant() noexcept {
+  const int f = forcedVariant();
+  return (f == kForceTensorCore || f == kForceNoTensorCore) ? -1 : f;
+}
 
 struct DeviceInfo {
   std::once_flag once;
@@ -166,7 +175,7 @@ static cudaError_t launchPolyMode(int variant, PolyParams& P, size_t smem, int d
 // Automatic choice: first variant of the preference list whose shared memory fits.
 static int choosePolyVariant(size_t D, size_t T, size_t nOut, int maxSmem, PolyGeom* geom,
                              bool doubleBuffered = false) noexcept {
-  const int forced = forcedVariant();
+  const int forced = forcedFfmaVariant();
   if (forced == -2) return -1;
   if (forced >= 0 && forced < kNumVariants) {
     return (polyGeometry(kVariants[forced], D, T, geom) && geom->smemBytes <= (size_t)maxSmem) ? forced : -1;
@@ -318,7 +327,7 @@ static int chooseTmaVariant(const FirCall& c, int maxSmem, TmaGeom* geom) noexce
   if ((uintptr_t)c.input % 16 != 0) return -1;                       // TMA needs a 16-byte aligned base
   if (c.numChannels > 1 && (c.inputStride % 2) != 0) return -1;       // ... and 16-byte strides
   if (c.numChannels > 0x7fffffffull) return -1;
-  const int forced = forcedVariant();
+  const int forced = forcedFfmaVariant();
   if (forced >= kNumVariants) {
     const int id = forced - kNumVariants;
     return tmaVariantFits(id, c, maxSmem, geom) ? id : -1;
@@ -398,7 +407,7 @@ static int chooseCcVariant(const FirCall& c, int maxSmem, TmaGeom* geom) noexcep
     return id >= 0 && id < kNumCcVariants && ccGeometry(kCcVariants[id], c.decimation, c.tapCount, g) &&
            g->smemBytes <= (size_t)maxSmem;
   };
-  const int forced = forcedVariant();
+  const int forced = forcedFfmaVariant();
   if (forced >= firstCcVariantId()) return fits(forced - firstCcVariantId(), geom) ? forced - firstCcVariantId() : -1;
   if (forced != -1) return -1;
   static const int orderNarrow[] = {0, 1, 3, 2};
@@ -551,7 +560,7 @@ static int chooseRealVariant(const FirCall& c, int maxSmem, RealGeom* geom) noex
   if (c.numChannels > 1 && (c.inputStride % 4) != 0) return -1;   // ... in every channel
   if (c.numChannels > 0x7fffffffull) return -1;
   const int firstId = kNumVariants + kNumTmaVariants + kNumSpecVariants;
-  const int forced = forcedVariant();
+  const int forced = forcedFfmaVariant();
   if (forced >= firstId) return realVariantFits(forced - firstId, c, maxSmem, geom) ? forced - firstId : -1;
   if (forced != -1) return -1;
   // decimation 1 (one branch pair, half the FFMA2s per tile of the complex kernel) is faster on the cp.async kernel:
@@ -585,7 +594,7 @@ static int chooseCfVariant(const FirCall& c, int maxSmem, RealGeom* geom) noexce
     return id >= 0 && id < kNumCfVariants && realGeometry(kCfVariants[id], c.decimation, c.tapCount, g, 2) &&
            g->smemBytes <= (size_t)maxSmem;
   };
-  const int forced = forcedVariant();
+  const int forced = forcedFfmaVariant();
   if (forced >= firstCfVariantId()) return fits(forced - firstCfVariantId(), geom) ? forced - firstCfVariantId() : -1;
   if (forced != -1) return -1;
   // tools/sweep.py --kind cf: 63 complex taps, D = 5, 2^27 samples: id 2 0.321 ms, id 3 0.349, id 0 0.353, id 1 0.381
@@ -703,6 +712,51 @@ static cudaError_t launchDirectNco(const FirCall& c, cudaStream_t stream) noexce
 
 static size_t outElemBytes(FirType t) noexcept { return t == kFirFF ? 4 : 8; }
 
+// ---------------------------------------------------------------------------------------------------------
+// Tensor-core path (fir_tc_kernel.cuh): FC, decimation 4 / 8 / 16, about 32 taps per output
+// ---------------------------------------------------------------------------------------------------------
+#ifdef GSDR_B200_TUNING
+size_t tcSharedBytes(unsigned D, unsigned tablePitch) noexcept;
+cudaError_t launchTc(unsigned D, TcParams& P, int dev, int smCount, cudaStream_t stream) noexcept;
+
+// Tiles of 1024 outputs per channel when the call qualifies for the tensor-core kernel, else 0.
+static unsigned long long tcTilesPerChannel(const FirCall& c, int maxSmem, TcParams* P) noexcept {
+  if (c.type != kFirFC || c.nco != kNcoNone) return 0;
+  // Measured and NOT adopted (profiles/r02_tc_*): 0.224 ms against the FFMA2 kernel's 0.166 ms on
+  // BASELINE config 2.  The kernel stays reachable through the tuning build's override only.
+  if (forcedVariant() != kForceTensorCore) return 0;
+  const size_t D = c.decimation, T = c.tapCount;
+  if (D != 4 && D != 8 && D != 16) return 0;
+  const size_t SD = (size_t)kTcS * D;
+  if (T > SD + D) return 0;                                // a window must fit two segments
+  if ((uintptr_t)c.input % 16 != 0) return 0;             // bulk copies need 16-byte aligned sources
+  if (c.numChannels > 1 && (c.tapStride != 0 || (c.inputStride % 2) != 0)) return 0;
+  const unsigned long long tiles = (c.numOutputs + kTcTileOut - 1) / kTcTileOut;
+  if (tiles * c.numChannels > 0x7fffffffull) return 0;
+  const unsigned K = (unsigned)((kTcS - 1) * D + T);
+  P->numStages = (K + 15u) / 16u;
+  P->aMax = (8u * (2u * P->numStages - 1u)) / (unsigned)D;
+  P->tablePitch = (P->aMax + kTcS) * 16u;
+  if (tcSharedBytes((unsigned)D, P->tablePitch) > (size_t)maxSmem) return 0;
+  return tiles;
+}
+
+static cudaError_t launchTcTiles(const FirCall& c, unsigned long long tiles, TcParams& P, int dev, int smCount,
+                                 cudaStream_t stream) noexcept {
+  P.x = (const float2*)c.input;
+  P.h = (const float*)c.taps;
+  P.y = (float2*)c.output;
+  P.xStride = c.inputStride;
+  P.yStride = c.outputStride;
+  P.nOut = c.numOutputs;
+  P.nIn = (unsigned long long)(c.numOutputs - 1) * c.decimation + c.tapCount;
+  P.tilesPerChannel = (unsigned)tiles;
+  P.totalTiles = (unsigned)(tiles * c.numChannels);
+  P.T = (unsigned)c.tapCount;
+  return launchTc((unsigned)c.decimation, P, dev, smCount, stream);
+}
+#endif  // GSDR_B200_TUNING
+
 cudaError_t enqueueFir(const FirCall& c, cudaStream_t stream) noexcept {
   if (c.numOutputs == 0 || c.numChannels == 0) return cudaSuccess;
   if (c.decimation == 0) return cudaErrorInvalidValue;
@@ -722,6 +776,13 @@ cudaError_t enqueueFir(const FirCall& c, cudaStream_t stream) noexcept {
   const DeviceInfo* info = deviceInfo(dev);
   if (!info || info->status != cudaSuccess) return info ? info->status : cudaErrorInvalidDevice;
 
+#ifdef GSDR_B200_TUNING
+  {
+    TcParams tp{};
+    const unsigned long long tcTiles = tcTilesPerChannel(c, info->maxSmemOptin, &tp);
+    if (tcTiles > 0) return launchTcTiles(c, tcTiles, tp, dev, info->smCount, stream);
+  }
+#endif
   {
     TmaGeom tg{};
     const int tv = chooseTmaVariant(c, info->maxSmemOptin, &tg);
@@ -812,7 +873,7 @@ cudaError_t enqueueFirInt8(bool nco, float sampleRate, float frequencyShift, siz
   if (!info || info->status != cudaSuccess) return info ? info->status : cudaErrorInvalidDevice;
   const size_t D = decimation, T = tapCount;
   const unsigned long long nIn = (unsigned long long)(numOutputs - 1) * D + T;
-  const int forced = forcedVariant();
+  const int forced = forcedFfmaVariant();
 
   if (forced != -2 && tmaSupportedDecimation(D) && (uintptr_t)input % 16 == 0) {
     const size_t J = (T + D - 1) / D;
@@ -1010,7 +1071,7 @@ GSDR_C_LINKAGE cudaError_t gsdrAdjustFrequencyFirFCInt8(float sampleRate, float 
 
 #ifdef GSDR_B200_TUNING
 GSDR_C_LINKAGE int gsdrB200SetKernelVariant(int variant) GSDR_NO_EXCEPT {
-  if (variant < -2 || variant >= firstCfVariantId() + kNumCfVariants) return -1;
+  if (variant < -4 || variant >= firstCfVariantId() + kNumCfVariants) return -1;
   gForcedVariant.store(variant, std::memory_order_relaxed);
   return 0;
 }
@@ -1048,6 +1109,23 @@ GSDR_C_LINKAGE int gsdrB200DescribeKernel(int firType, size_t decimation, size_t
     probe.decimation = decimation;
     probe.tapCount = tapCount;
     probe.numOutputs = numOutputs;
+#ifdef GSDR_B200_TUNING
+    if (firType == kFirFC) {
+      TcParams tp{};
+      const unsigned long long tiles = tcTilesPerChannel(probe, di->maxSmemOptin, &tp);
+      if (tiles > 0) {
+        info->variant = firstCfVariantId() + kNumCfVariants;  // == gsdrB200NumKernelVariants(): the tensor-core kernel
+        info->outputsPerThread = 0;
+        info->threadsPerBlock = kTcThreads;
+        info->phaseGroups = 1;
+        info->windowBuffers = 1;
+        info->outputsPerBlock = kTcTileOut;
+        info->sharedBytesPerBlock = tcSharedBytes((unsigned)decimation, tp.tablePitch);
+        info->numBlocks = (size_t)tiles;
+        return 0;
+      }
+    }
+#endif
     TmaGeom tg{};
     const int tv = chooseTmaVariant(probe, di->maxSmemOptin, &tg);
     if (tv >= 0) {

@@ -1,0 +1,133 @@
+"""The tensor-core FIR (gsdr_b200/csrc/fir_tc_kernel.cuh: banded-Toeplitz TF32 GEMM with hi/lo operand splitting)
+against the oracle: BASELINE tolerance max|err| <= 1e-5 * sum|h| * max|x| (FP32-grade, accumulation order differs
+from ref: src/fir.cu:57-70), ragged ends, batched channels, and the position independence that keeps time shards
+bit-identical to the unsharded call."""
+import numpy as np
+import pytest
+import torch
+
+import gsdr_b200 as g
+from gsdr_b200 import synth
+from oracle import oracle
+
+pytestmark = pytest.mark.gpu
+
+TC = -4       # gsdrB200SetKernelVariant: tensor-core kernel wherever its shape rules allow (tuning build)
+NO_TC = -3    # automatic choice among the FFMA2 kernels only
+
+
+def _tol(taps, x):
+    return 1e-5 * float(np.abs(taps).sum()) * float(np.abs(x).max())
+
+
+def _run_fc(D, taps, dx, n_out, dev):
+    y = torch.full((n_out + 16,), float("nan"), dtype=torch.complex64, device=dev)
+    g.gsdrFirFC(D, torch.from_numpy(taps).to(dev), taps.shape[0], dx, y[8:], n_out, 0, None)
+    torch.cuda.synchronize()
+    out = y.cpu().numpy()
+    assert np.isnan(out[:8].real).all() and np.isnan(out[8 + n_out:].real).all(), "wrote outside the output"
+    return out[8:8 + n_out]
+
+
+def test_tensor_core_kernel_is_opt_in_only(cuda_device):
+    """Measured slower than the FFMA2 kernels, so no shape selects it by default; the tuning
+    build's override reaches it for the shapes its layout supports."""
+    tc_id = g.num_kernel_variants()
+    assert g.describe_kernel(0, 8, 255, 8_388_577).variant != tc_id      # BASELINE config 2, release library
+    g.set_kernel_variant(TC)
+    assert g.describe_kernel(0, 8, 255, 8_388_577).variant == tc_id
+    assert g.describe_kernel(0, 4, 127, 1_048_545).variant == tc_id      # config 4 (per channel)
+    assert g.describe_kernel(0, 32, 1023, 8_388_577).variant != tc_id    # segments would not fit shared memory
+    assert g.describe_kernel(0, 10, 255, 8_388_577).variant != tc_id     # k-groups of four would straddle rows
+
+
+@pytest.mark.parametrize("D,T,n_out", [
+    (8, 255, 200_000), (8, 255, 65_536), (8, 255, 66_561), (8, 264, 70_001), (8, 193, 80_003), (8, 1, 70_000),
+    (4, 127, 150_001), (4, 132, 66_000), (4, 97, 99_999), (16, 511, 70_000), (16, 528, 65_537), (16, 400, 66_666)])
+def test_tensor_core_fir_against_oracle(D, T, n_out, cuda_device):
+    taps = synth.random_taps(T, 100 + D)           # asymmetric: catches tap-order and band-offset mistakes
+    n_in = g.fir_num_inputs(n_out, T, D)
+    x = synth.tone_plus_noise(0, n_in, seed=200 + T)
+    g.set_kernel_variant(TC)
+    assert g.describe_kernel(0, D, T, n_out).variant == g.num_kernel_variants()
+    y = _run_fc(D, taps, torch.from_numpy(x).to(cuda_device), n_out, cuda_device)
+    want = oracle.fir("fc", D, taps, x, n_out, f64=True)
+    err = np.abs(y - want).max()
+    assert err <= _tol(taps, x), f"max|err| {err} > {_tol(taps, x)}"
+    # FP32-grade, not TF32-grade: the split must leave an error comparable to the FFMA2 kernel's
+    g.set_kernel_variant(NO_TC)
+    y2 = _run_fc(D, taps, torch.from_numpy(x).to(cuda_device), n_out, cuda_device)
+    err2 = np.abs(y2 - want).max()
+    assert err <= max(8.0 * err2, 0.2 * _tol(taps, x))
+
+
+def test_impulse_and_dc_known_answers_on_tensor_cores(cuda_device):
+    D, T, n_out = 8, 255, 70_000
+    n_in = g.fir_num_inputs(n_out, T, D)
+    taps = (np.arange(T, dtype=np.float32) + 1.0) / 64.0
+    g.set_kernel_variant(TC)
+    for k in (0, 7, 8, 254, 255, 256, 100_003, n_in - 1):
+        x = np.zeros(n_in, dtype=np.complex64)
+        x[k] = 3.0 - 2.0j
+        y = _run_fc(D, taps, torch.from_numpy(x).to(cuda_device), n_out, cuda_device)
+        want = np.zeros(n_out, dtype=np.complex64)
+        for n in range(max(0, (k - T) // D), min(n_out, k // D + 1)):
+            i = k - n * D
+            if 0 <= i < T:
+                want[n] = taps[i] * x[k]
+        assert np.array_equal(y, want), f"impulse at {k}"   # exactly representable products: the split loses nothing
+    ones = np.ones(n_in, dtype=np.complex64) * (1.0 + 0.5j)
+    y = _run_fc(D, taps, torch.from_numpy(ones).to(cuda_device), n_out, cuda_device)
+    assert np.abs(y - taps.astype(np.float64).sum() * (1.0 + 0.5j)).max() <= _tol(taps, ones)
+
+
+def test_batched_channels_on_tensor_cores_equal_single_calls_bit_exact(cuda_device):
+    D, T, C, n_in = 4, 127, 6, 300_000
+    n_out = g.fir_num_outputs(n_in, T, D)
+    taps = synth.lowpass_taps(T, D)
+    xs = synth.tone_plus_noise(0, C * n_in, seed=301, device=cuda_device).view(C, n_in)
+    dt = torch.from_numpy(taps).to(cuda_device)
+    g.set_kernel_variant(TC)
+    yb = torch.zeros((C, n_out + 3), dtype=torch.complex64, device=cuda_device)
+    g.gsdrFirFCBatched(D, dt, T, 0, xs, n_in, yb, n_out + 3, n_out, C, 0, None)
+    for c in range(C):
+        one = torch.zeros(n_out, dtype=torch.complex64, device=cuda_device)
+        g.gsdrFirFC(D, dt, T, xs[c], one, n_out, 0, None)
+        torch.cuda.synchronize()
+        assert torch.equal(one, yb[c, :n_out])
+    assert float(yb[:, n_out:].abs().max()) == 0.0
+    want = oracle.fir("fc", D, taps, xs[C - 1].cpu().numpy(), n_out, f64=True)
+    assert np.abs(yb[C - 1, :n_out].cpu().numpy() - want).max() <= _tol(taps, xs[C - 1].cpu().numpy())
+
+
+@pytest.mark.parametrize("shards", [2, 3, 8])
+def test_tensor_core_results_do_not_depend_on_the_position_in_the_call(shards, cuda_device):
+    """Every output goes through the same arithmetic wherever it sits in a tile or a window, so a time-sharded run
+    (shards start at arbitrary output indices) reproduces the unsharded call bit for bit."""
+    D, T, n_in = 8, 255, 3_000_017
+    taps = synth.lowpass_taps(T, D)
+    x = synth.tone_plus_noise(0, n_in, seed=302, device=cuda_device)
+    n_out = g.fir_num_outputs(n_in, T, D)
+    dt = torch.from_numpy(taps).to(cuda_device)
+    g.set_kernel_variant(TC)
+    whole = torch.zeros(n_out, dtype=torch.complex64, device=cuda_device)
+    g.gsdrFirFC(D, dt, T, x, whole, n_out, 0, None)
+    parts = torch.zeros_like(whole)
+    for s in range(shards):
+        sh = g.shard_plan_time(n_out, D, T, 0, shards, s)
+        xs = x[sh.firstInput: sh.firstInput + sh.numInputs].clone()   # a fresh, 16-byte aligned shard buffer
+        g.gsdrFirFC(D, dt, T, xs, parts[sh.firstOutput: sh.firstOutput + sh.numOutputs], sh.numOutputs, 0, None)
+    torch.cuda.synchronize()
+    assert torch.equal(whole, parts)
+
+
+def test_unaligned_input_falls_back_and_still_matches(cuda_device):
+    g.set_kernel_variant(TC)
+    D, T, n_out = 8, 255, 100_000
+    n_in = g.fir_num_inputs(n_out, T, D)
+    taps = synth.lowpass_taps(T, D)
+    x = synth.tone_plus_noise(0, n_in + 1, seed=303)
+    dx = torch.from_numpy(x).to(cuda_device)[1:]   # 8-byte aligned only: bulk copies are not possible
+    y = _run_fc(D, taps, dx, n_out, cuda_device)
+    want = oracle.fir("fc", D, taps, x[1:], n_out, f64=True)
+    assert np.abs(y - want).max() <= _tol(taps, x)
