@@ -104,6 +104,20 @@ static constexpr TmaVariant kCcVariants[] = {
 };
 static constexpr int kNumCcVariants = (int)(sizeof(kCcVariants) / sizeof(kCcVariants[0]));
 
+// Segment-pipelined kernel for wide rows (firTmaWideKernel): X(id, TG, PSPLIT, MIXW, MINB); global ids continue after
+// the real-input x complex-tap variants.  MIXW = 1: plain FIR (the extra warp only issues the tensor copies).
+#define GSDR_WIDE_VARIANTS(X) \
+  X(0, 64, 4, 1, 1)           \
+  X(1, 64, 4, 4, 1)           \
+  X(2, 64, 4, 2, 1)
+
+static constexpr SpecVariant kWideVariants[] = {
+#define X(id, tg, ps, mw, mb) {tg, ps, mw, mb},
+    GSDR_WIDE_VARIANTS(X)
+#undef X
+};
+static constexpr int kNumWideVariants = (int)(sizeof(kWideVariants) / sizeof(kWideVariants[0]));
+
 template <int MODE, int TG, int PSPLIT, int DT, int NBUF, int MINB>
 static cudaError_t launchTmaT(const CUtensorMap& map, TmaParams& P, size_t smem, int dev, int smCount,
                               cudaStream_t stream) noexcept {
@@ -182,6 +196,39 @@ static cudaError_t launchSpecT(const CUtensorMap& map, TmaParams& P, size_t smem
   P.strideTile = grid % P.tilesPerChannel;
   void* args[] = {(void*)&map, (void*)&P};
   return cudaLaunchKernel((const void*)kernel, dim3(grid), dim3(kThreads), args, smem, stream);
+}
+
+template <int MODE, int TG, int PSPLIT, int DT, int MIXW, int MINB>
+static cudaError_t launchWideT(const CUtensorMap& map, TmaParams& P, size_t smem, int dev, int smCount,
+                               cudaStream_t stream) noexcept {
+  static std::atomic<size_t> configured[64];
+  auto kernel = firTmaWideKernel<MODE, TG, PSPLIT, DT, MIXW, MINB>;
+  constexpr int kThreads = TG * PSPLIT + 32 * MIXW;
+  if (smem > configured[dev & 63].load(std::memory_order_acquire)) {
+    cudaError_t st = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (st != cudaSuccess) return report(st, "cudaFuncSetAttribute(MaxDynamicSharedMemorySize)");
+    configured[dev & 63].store(smem, std::memory_order_release);
+  }
+  // two 72 KB stage buffers: one CTA per SM
+  const unsigned grid = (unsigned)(P.totalTiles < (unsigned)smCount ? P.totalTiles : (unsigned)smCount);
+  P.strideChan = grid / P.tilesPerChannel;
+  P.strideTile = grid % P.tilesPerChannel;
+  void* args[] = {(void*)&map, (void*)&P};
+  return cudaLaunchKernel((const void*)kernel, dim3(grid), dim3(kThreads), args, smem, stream);
+}
+
+template <int DT>
+static cudaError_t launchWideD(int mode, int variant, const CUtensorMap& map, TmaParams& P, size_t smem, int dev,
+                               int smCount, cudaStream_t stream) noexcept {
+  switch (variant) {
+#define X(id, tg, ps, mw, mb)                                                                                      \
+  case id:                                                                                                         \
+    return mode == kPolyFC ? launchWideT<kPolyFC, tg, ps, DT, mw, mb>(map, P, smem, dev, smCount, stream)          \
+                           : launchWideT<kPolyNcoExact, tg, ps, DT, mw, mb>(map, P, smem, dev, smCount, stream);
+    GSDR_WIDE_VARIANTS(X)
+#undef X
+    default: return cudaErrorInvalidValue;
+  }
 }
 
 template <int DT>
@@ -375,6 +422,12 @@ static cudaError_t launchInt8D(int variant, Int8Params& P, size_t smem, int dev,
 #define GSDR_DECLARE_TMA_DT(DT) cudaError_t launchTmaDt##DT(int mode, int variant, GSDR_TMA_ARGS) noexcept;
 #define GSDR_DECLARE_SPEC_DT(DT) cudaError_t launchSpecDt##DT(int variant, GSDR_TMA_ARGS) noexcept;
 #define GSDR_DECLARE_CC_DT(DT) cudaError_t launchCcDt##DT(int variant, GSDR_TMA_ARGS) noexcept;
+#define GSDR_DECLARE_WIDE_DT(DT) cudaError_t launchWideDt##DT(int mode, int variant, GSDR_TMA_ARGS) noexcept;
+#define GSDR_DEFINE_WIDE_DT(DT)                                                  \
+  cudaError_t launchWideDt##DT(int mode, int variant, GSDR_TMA_ARGS) noexcept {  \
+    return launchWideD<DT>(mode, variant, map, P, smem, dev, smCount, stream);   \
+  }
+GSDR_DECLARE_WIDE_DT(32)
 #define GSDR_DECLARE_REAL_DT(DT) cudaError_t launchRealDt##DT(int variant, GSDR_REAL_ARGS) noexcept;
 GSDR_DECLARE_TMA_DT(0) GSDR_DECLARE_TMA_DT(4) GSDR_DECLARE_TMA_DT(8) GSDR_DECLARE_TMA_DT(10) GSDR_DECLARE_TMA_DT(32)
 GSDR_DECLARE_SPEC_DT(0) GSDR_DECLARE_SPEC_DT(8) GSDR_DECLARE_SPEC_DT(10) GSDR_DECLARE_SPEC_DT(32)

@@ -1521,4 +1521,276 @@ __global__ void __launch_bounds__(TG* PSPLIT + 32 * MIXW, MINB) firTmaInt8Kernel
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Wide rows (D a multiple of 16 above 16: rows of more than 128 bytes, BASELINE config 3), with or without the
+// exact NCO.  firTmaKernel / firTmaNcoSpecKernel hold a whole window (all 128-byte row segments) per buffer: at
+// D = 32 that is 74 KB per 256-output tile, so a double-buffered CTA is alone on its SM with FOUR filter warps — one
+// per scheduler, nobody to hide its latencies (FIR-only 0.757 ms against 0.645 ms with eight warps per SM;
+// profiles/r02/sweep_fc_d32.jsonl) — and the single-buffered variant with two CTAs per SM cannot overlap the copy
+// (0.76 ms).  Here the pipeline stage is ONE SEGMENT of a tile: a buffer holds the 8 branch pairs of one 128-byte
+// segment for 512 outputs (8 planes x 72 row groups x 128 B = 72 KB), two buffers alternate, and the EIGHT filter
+// warps (64 threads x 4 branch groups) keep their accumulators in registers across the segments of a tile; partial
+// sums are exchanged and outputs stored after the last one.  Halo rows drop from 12.5 % to 6 % of a tile, the next
+// segment is always in flight (TMA, one tensor copy per stage), and with the NCO the mixer warps work one stage
+// ahead exactly as in firTmaNcoSpecKernel (row anchors are computed once per tile, at its first segment).
+//   fullRaw[b]  TMA bytes of buffer b have landed            (tx count, armed by producer thread 0)
+//   fullMix[b]  buffer b is mixed (NCO only)                  (every producer thread arrives)
+//   empty[b]    the filter warps are done reading buffer b    (every filter thread arrives)
+// One tap set for all channels (hStride == 0); compile-time decimation only.
+// ---------------------------------------------------------------------------------------------------------
+template <int NT, int DT>
+__device__ __forceinline__ void tmaStageSlowSegment(unsigned char* stageBuf, unsigned sg, const float2* src,
+                                                    unsigned long long in0, unsigned rows, unsigned planeBytes,
+                                                    unsigned long long nIn, const TmaParams& P, unsigned lt) {
+  constexpr unsigned D = DT;
+  const unsigned total = rows * 16u;  // 16 samples (8 branch pairs) of every row
+  for (unsigned s = lt; s < total; s += NT) {
+    const unsigned m = s >> 4, p = 16u * sg + (s & 15u);
+    const unsigned long long g = in0 + (unsigned long long)m * D + p;
+    const bool valid = g < nIn;
+    // tmaSampleOffset addresses the whole-window layout: take the segment's base out again
+    cpAsync8z(stageBuf + tmaSampleOffset<DT>(m, p, planeBytes, P) - sg * 8u * planeBytes, src + (valid ? g : 0ull), valid);
+  }
+}
+
+// exact-NCO mix of one landed segment (phases 16*sg .. 16*sg + 15 of every row); arithmetic as in tmaMixRowsStatic
+template <int NT, int DT>
+__device__ __forceinline__ void tmaMixSegmentStatic(unsigned char* stageBuf, unsigned sg, unsigned mhCount,
+                                                    unsigned planeBytes, const float2* ncoA, const float2* ncoR,
+                                                    const TmaParams& P, unsigned lt) {
+  constexpr unsigned CH = 4, CHUNKS = 2, G = NT / 8;
+  static_assert(NT % 16 == 0, "two chunk lanes per residue");
+  constexpr unsigned V_LANES = G / CHUNKS;
+  const unsigned s = lt & 7u;
+  const unsigned rest = lt >> 3;
+  const unsigned ck = rest % CHUNKS, vLane = rest / CHUNKS;
+  const unsigned sw = tmaSwizzle<DT>(s, P);
+  const unsigned vTotal = 8u * ((mhCount + 7u) >> 3);
+  const unsigned pp0 = 8u * sg + ck * CH;  // first branch pair of this thread's chunk
+  float2 r[2 * CH];
+  unsigned off[CH];
+#pragma unroll
+  for (unsigned j = 0; j < CH; j++) {
+    const float4 rr = *reinterpret_cast<const float4*>(ncoR + 2u * (pp0 + j));
+    r[2 * j] = make_float2(rr.x, rr.y);
+    r[2 * j + 1] = make_float2(rr.z, rr.w);
+    off[j] = ((ck * CH + j) ^ sw) << 4;
+  }
+  unsigned char* base = stageBuf + s * 128u;
+  const float2* anchors = ncoA + s;
+  for (unsigned v = vLane; v < vTotal; v += V_LANES) {
+    const unsigned ml = v & 7u, u = v >> 3;
+    if (s + 8u * u >= mhCount) continue;
+    const float2 an = anchors[ml * mhCount + 8u * u];
+    unsigned char* row = base + ml * planeBytes + u * 1024u;
+    float4 x[CH];
+#pragma unroll
+    for (unsigned j = 0; j < CH; j++) x[j] = *reinterpret_cast<const float4*>(row + off[j]);
+#pragma unroll
+    for (unsigned j = 0; j < CH; j++) {
+      const float2 w0 = cmulf(an, r[2 * j]);
+      const float2 w1 = cmulf(an, r[2 * j + 1]);
+      const float2 a = cmulf(make_float2(x[j].x, x[j].y), w0);
+      const float2 c = cmulf(make_float2(x[j].z, x[j].w), w1);
+      *reinterpret_cast<float4*>(row + off[j]) = make_float4(a.x, a.y, c.x, c.y);
+    }
+  }
+}
+
+template <int MODE, int TG, int PSPLIT, int DT, int MIXW, int MINB>
+__global__ void __launch_bounds__(TG* PSPLIT + 32 * MIXW, MINB)
+    firTmaWideKernel(const __grid_constant__ CUtensorMap map, const TmaParams P) {
+  static_assert(DT >= 32 && DT % 16 == 0, "rows of at least two 128-byte segments, compile-time decimation");
+  static_assert(MODE == kPolyFC || MODE == kPolyNcoExact, "plain FIR or the exact NCO");
+  static_assert(8 % PSPLIT == 0, "the branch groups split the 8 pairs of a segment");
+  constexpr unsigned NTF = TG * PSPLIT;  // filter threads
+  constexpr unsigned NTM = 32 * MIXW;    // producer threads
+  constexpr unsigned BOUT = kTmaR * TG;
+  constexpr unsigned D = DT;
+  constexpr unsigned numSegs = D / 16;
+  constexpr unsigned planeBytes = tmaPlaneRows(TG, kTmaJpadCap, DT) * 128u;
+  constexpr unsigned stageBytes = 8u * planeBytes;
+  constexpr bool kNco = MODE == kPolyNcoExact;
+  // Stage buffers.  Plain FIR: two (the copy of the next segment runs under the FIR of this one).  NCO: three —
+  // landing, being mixed, being filtered — because copy (1.6 us for 72 KB at an SM's share of HBM) PLUS mix no longer
+  // fit under one FIR stage (3 us); the partial-sum exchange lives in the stage buffer the tile has just finished
+  // with, so three buffers fit the 227 KB.
+  constexpr unsigned NBUF = kNco ? 3u : 2u;
+  extern __shared__ __align__(16) unsigned char smemRaw[];
+  __shared__ __align__(8) unsigned long long fullRaw[NBUF], fullMix[NBUF], emptyBar[NBUF];
+  unsigned char* bufBase = smemRaw + ((1024u - (smemU32(smemRaw) & 1023u)) & 1023u);
+  float* hs = reinterpret_cast<float*>(bufBase + NBUF * stageBytes);
+  float2* ncoA = reinterpret_cast<float2*>(hs + (size_t)D * P.Jpad + 32u);
+  float2* ncoR = ncoA + (BOUT + P.Jpad);
+
+  const unsigned tid = threadIdx.x;
+  const unsigned rowsStaged = BOUT + P.Jpad;
+  if (tid == 0) {
+    for (unsigned b = 0; b < NBUF; b++) {
+      mbarInit(&fullRaw[b], 1);
+      mbarInit(&fullMix[b], NTM);
+      mbarInit(&emptyBar[b], NTF);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (kNco) {
+    for (unsigned p = tid; p < D; p += NTF + NTM) ncoR[p] = ncoExactPhasor((unsigned long long)p, P.ncoStep);
+  }
+  {
+    const unsigned nh = D * P.Jpad;
+    for (unsigned i = tid; i < nh + 32u; i += NTF + NTM) {
+      const unsigned pp = i / (2u * P.Jpad);
+      const unsigned rem = i - pp * 2u * P.Jpad;
+      const unsigned ti = (rem >> 1) * D + 2u * pp + (rem & 1u);
+      hs[i] = (i < nh && ti < P.T) ? __ldg(P.h + ti) : 0.0f;
+    }
+  }
+  __syncthreads();
+
+  unsigned chan = blockIdx.x / P.tilesPerChannel;
+  unsigned tile = blockIdx.x - chan * P.tilesPerChannel;
+  auto advance = [&](unsigned& c, unsigned& tl) {
+    c += P.strideChan;
+    tl += P.strideTile;
+    if (tl >= P.tilesPerChannel) {
+      tl -= P.tilesPerChannel;
+      c += 1;
+    }
+  };
+  auto tileIsFast = [&](unsigned tl) -> bool { return tl * BOUT + rowsStaged <= P.tmaRows; };
+
+  if (tid >= NTF) {
+    // ===================== producer warps =====================
+    const unsigned lt = tid - NTF;
+    // fetch of one stage: wait until the filter warps have left the buffer's previous use, then one tensor copy
+    // (or, for the last tile of a channel, guarded cp.async by all producer threads)
+    auto fetch = [&](unsigned c, unsigned tl, unsigned sg, unsigned b, unsigned use) {
+      unsigned char* buf = bufBase + b * stageBytes;
+      if (use > 0) mbarWait(&emptyBar[b], (use - 1u) & 1u);
+      if (tileIsFast(tl)) {
+        if (lt == 0) {
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          mbarExpectTx(&fullRaw[b], stageBytes);
+          tmaLoad4(buf, &map, &fullRaw[b], (int)(sg * 32u), (int)(tl * (BOUT / 8)), 0, (int)c);
+        }
+      } else {
+        tmaStageSlowSegment<NTM, DT>(buf, sg, P.x + (size_t)c * P.xStride, (unsigned long long)tl * BOUT * D, rowsStaged,
+                                     planeBytes, P.nIn, P, lt);
+        asm volatile("cp.async.commit_group;\n" ::: "memory");
+        asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+        mixBarrier<NTM, 1>();
+        if (lt == 0) mbarArrive(&fullRaw[b]);  // completes the phase the consumers of this stage wait for
+      }
+    };
+    if (!kNco) {
+      unsigned b = 0, use = 0;
+      for (; chan < P.numChannels; advance(chan, tile)) {
+        for (unsigned sg = 0; sg < numSegs; sg++) {
+          fetch(chan, tile, sg, b, use);
+          if (++b == NBUF) b = 0, use++;
+        }
+      }
+      return;
+    }
+    // NCO: the copy of stage v + 1 is issued before stage v is mixed
+    unsigned nChan = chan, nTile = tile, nSg = 0, nb = 0, nUse = 0;  // cursor of the next stage to fetch
+    auto fetchNext = [&]() {
+      if (nChan >= P.numChannels) return;
+      fetch(nChan, nTile, nSg, nb, nUse);
+      if (++nb == NBUF) nb = 0, nUse++;
+      if (++nSg == numSegs) {
+        nSg = 0;
+        advance(nChan, nTile);
+      }
+    };
+    fetchNext();
+    unsigned b = 0, use = 0;
+    const unsigned mhCount = rowsStaged >> 3;
+    for (; chan < P.numChannels; advance(chan, tile)) {
+      const unsigned long long in0 = (unsigned long long)tile * BOUT * D;
+      for (unsigned sg = 0; sg < numSegs; sg++) {
+        fetchNext();
+        unsigned char* buf = bufBase + b * stageBytes;
+        mbarWait(&fullRaw[b], use & 1u);
+        if (sg == 0) {  // row anchors of the tile, stored [ml][mh]
+          for (unsigned m = lt; m < rowsStaged; m += NTM) {
+            ncoA[(m & 7u) * mhCount + (m >> 3)] = ncoExactPhasor(P.ncoFirst + in0 + (unsigned long long)m * D, P.ncoStep);
+          }
+          mixBarrier<NTM, 1>();
+        }
+        tmaMixSegmentStatic<NTM, DT>(buf, sg, mhCount, planeBytes, ncoA, ncoR, P, lt);
+        mbarArrive(&fullMix[b]);  // release: the mixed segment is visible to whoever acquires the barrier
+        if (sg + 1 == numSegs) mixBarrier<NTM, 1>();  // ncoA may be overwritten by the next tile's anchors
+        if (++b == NBUF) b = 0, use++;
+      }
+    }
+    return;
+  }
+
+  // ============================== filter warps ==============================
+  const unsigned grp = tid / TG;
+  const unsigned t = tid - grp * TG;
+  constexpr unsigned pairsPerGroup = 8 / PSPLIT;
+  unsigned b = 0, use = 0;
+  for (; chan < P.numChannels; advance(chan, tile)) {
+    const unsigned long long o0 = (unsigned long long)tile * BOUT;
+    float2 acc[kTmaR];
+#pragma unroll
+    for (int r = 0; r < kTmaR; r++) acc[r] = make_float2(0.0f, 0.0f);
+    unsigned lastB = 0;
+    for (unsigned sg = 0; sg < numSegs; sg++) {
+      // firComputePairs addresses the whole-window layout (segment sg starts 8 * sg planes in): shift the base back
+      const unsigned char* buf = bufBase + b * stageBytes - sg * stageBytes;
+      mbarWait(kNco ? &fullMix[b] : &fullRaw[b], use & 1u);
+      const unsigned ppBegin = 8u * sg + grp * pairsPerGroup;
+      firComputePairs<DT>(acc, buf, hs, t, ppBegin, ppBegin + pairsPerGroup, P.Jpad, planeBytes, P);
+      lastB = b;
+      if (sg + 1 < numSegs || PSPLIT == 1) mbarArrive(&emptyBar[b]);  // no more reads of the stage by this thread
+      if (++b == NBUF) b = 0, use++;
+    }
+    if (PSPLIT > 1) {
+      // partial sums of the branch groups go through the stage buffer the tile has just finished with
+      float4* red = reinterpret_cast<float4*>(bufBase + lastB * stageBytes);
+      asm volatile("bar.sync 2, %0;" ::"n"(NTF) : "memory");  // every filter thread has left the window
+      if (grp > 0) {
+#pragma unroll
+        for (int q = 0; q < kTmaR / 2; q++) {
+          red[((grp - 1) * (kTmaR / 2) + q) * TG + t] =
+              make_float4(acc[2 * q].x, acc[2 * q].y, acc[2 * q + 1].x, acc[2 * q + 1].y);
+        }
+      }
+      asm volatile("bar.sync 2, %0;" ::"n"(NTF) : "memory");
+      if (grp == 0) {
+#pragma unroll
+        for (int g = 1; g < PSPLIT; g++) {
+#pragma unroll
+          for (int q = 0; q < kTmaR / 2; q++) {
+            const float4 w = red[((g - 1) * (kTmaR / 2) + q) * TG + t];
+            acc[2 * q].x += w.x;
+            acc[2 * q].y += w.y;
+            acc[2 * q + 1].x += w.z;
+            acc[2 * q + 1].y += w.w;
+          }
+        }
+      }
+      mbarArrive(&emptyBar[lastB]);  // the buffer may now be refilled
+    }
+    if (grp == 0) {
+      const unsigned long long ob = o0 + (unsigned long long)t * kTmaR;
+      float2* y = P.y + (size_t)chan * P.yStride;
+      if (P.y16 && ob + kTmaR <= P.nOut) {
+#pragma unroll
+        for (int r = 0; r < kTmaR; r += 2) {
+          *reinterpret_cast<float4*>(y + ob + r) = make_float4(acc[r].x, acc[r].y, acc[r + 1].x, acc[r + 1].y);
+        }
+      } else {
+#pragma unroll
+        for (int r = 0; r < kTmaR; r++) {
+          if (ob + r < P.nOut) y[ob + r] = acc[r];
+        }
+      }
+    }
+  }
+}
+
 }  // namespace gsdr_b200

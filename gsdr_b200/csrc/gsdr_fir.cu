@@ -374,6 +374,40 @@ static int chooseTmaVariant(const FirCall& c, int maxSmem, TmaGeom* geom) noexce
   return -1;
 }
 
+// ---- wide rows (D = 32), segment-pipelined: firTmaWideKernel ----
+static int firstWideVariantId() noexcept;
+
+static bool wideGeometry(const SpecVariant& v, size_t D, size_t T, bool nco, TmaGeom* g) noexcept {
+  if (D != 32) return false;  // the compile-time instantiations
+  TmaVariant shape{v.tg, v.psplit, 2, v.minBlocks};
+  if (!tmaGeometry(shape, D, T, g) || !g->staticD) return false;
+  // stage buffers (three with the NCO, two without; the partial-sum exchange reuses one), taps, row anchors + table
+  g->smemBytes = 1024 + (nco ? 3 : 2) * 8 * (size_t)g->planeBytes + (D * g->Jpad + 32) * 4 +
+                 ((size_t)kTmaR * v.tg + g->Jpad + D) * 8;
+  return true;
+}
+
+// Returns the wide-row variant for this call, or -1 when the call does not qualify.
+static int chooseWideVariant(const FirCall& c, int maxSmem, TmaGeom* geom) noexcept {
+  if (c.type != kFirFC || c.nco == kNcoLiteral) return -1;
+  if (c.numOutputs >= 0xfff00000ull || c.decimation != 32 || !encodeTiled()) return -1;
+  if ((uintptr_t)c.input % 16 != 0) return -1;
+  if (c.numChannels > 1 && ((c.inputStride % 2) != 0 || c.tapStride != 0)) return -1;
+  if (c.numChannels > 0x7fffffffull) return -1;
+  const bool nco = c.nco == kNcoExact;
+  auto fits = [&](int id, TmaGeom* g) {
+    return id >= 0 && id < kNumWideVariants && wideGeometry(kWideVariants[id], c.decimation, c.tapCount, nco, g) &&
+           g->smemBytes <= (size_t)maxSmem;
+  };
+  const int forced = forcedFfmaVariant();
+  if (forced >= firstWideVariantId()) return fits(forced - firstWideVariantId(), geom) ? forced - firstWideVariantId() : -1;
+  if (forced != -1) return -1;
+  // 512-output tiles on one CTA per SM: worth it once every SM gets a few tiles
+  if ((c.numOutputs + 511) / 512 * c.numChannels < 296) return -1;
+  const int id = 1;  // 64 x 4 filter threads + 4 producer warps for both (tools/sweep.py: plain FIR 0.649 vs 0.665 ms with 1)
+  return fits(id, geom) ? id : -1;
+}
+
 // ---- complex taps (gsdrFirCC): two tap planes on the same windows ----
 static bool ccGeometry(const TmaVariant& v, size_t D, size_t T, TmaGeom* g) noexcept {
   TmaVariant half = v;
@@ -425,10 +459,13 @@ static int chooseCcVariant(const FirCall& c, int maxSmem, TmaGeom* geom) noexcep
 
 // variant: a TMA / fused-NCO variant id, or (ccVariant >= 0) a complex-tap variant
 static cudaError_t launchTma(const FirCall& c, int variant, const TmaGeom& geom, int dev, int smCount,
-                             cudaStream_t stream, int ccVariant = -1) noexcept {
+                             cudaStream_t stream, int ccVariant = -1, int wideVariant = -1) noexcept {
   TmaVariant v;
   int mixw = 0;
-  if (ccVariant >= 0) {
+  if (wideVariant >= 0) {
+    if (wideVariant >= kNumWideVariants) return cudaErrorInvalidValue;
+    v = TmaVariant{kWideVariants[wideVariant].tg, kWideVariants[wideVariant].psplit, 2, 1};
+  } else if (ccVariant >= 0) {
     if (ccVariant >= kNumCcVariants) return cudaErrorInvalidValue;
     v = kCcVariants[ccVariant];
   } else if (!tmaVariantShape(variant, &v, &mixw)) {
@@ -491,6 +528,10 @@ static cudaError_t launchTma(const FirCall& c, int variant, const TmaGeom& geom,
       return cudaErrorInvalidValue;
     }
     if (tmaRows < 8) P.tmaRows = 0;
+  }
+  if (wideVariant >= 0) {
+    return launchWideDt32(c.nco == kNcoExact ? kPolyNcoExact : kPolyFC, wideVariant, map, P, geom.smemBytes, dev, smCount,
+                          stream);
   }
   if (ccVariant >= 0) {
     if (geom.staticD && D == 8) return launchCcDt8(ccVariant, map, P, geom.smemBytes, dev, smCount, stream);
@@ -582,6 +623,7 @@ static int chooseRealVariant(const FirCall& c, int maxSmem, RealGeom* geom) noex
 }
 
 static int firstCfVariantId() noexcept { return firstCcVariantId() + kNumCcVariants; }
+static int firstWideVariantId() noexcept { return firstCfVariantId() + kNumCfVariants; }
 
 // Returns the real-input x complex-taps variant for this call, or -1 when the call does not qualify.
 static int chooseCfVariant(const FirCall& c, int maxSmem, RealGeom* geom) noexcept {
@@ -785,6 +827,8 @@ cudaError_t enqueueFir(const FirCall& c, cudaStream_t stream) noexcept {
 #endif
   {
     TmaGeom tg{};
+    const int wv = chooseWideVariant(c, info->maxSmemOptin, &tg);
+    if (wv >= 0) return launchTma(c, -1, tg, dev, info->smCount, stream, -1, wv);
     const int tv = chooseTmaVariant(c, info->maxSmemOptin, &tg);
     if (tv >= 0) return launchTma(c, tv, tg, dev, info->smCount, stream);
     RealGeom rg{};
@@ -1071,7 +1115,7 @@ GSDR_C_LINKAGE cudaError_t gsdrAdjustFrequencyFirFCInt8(float sampleRate, float 
 
 #ifdef GSDR_B200_TUNING
 GSDR_C_LINKAGE int gsdrB200SetKernelVariant(int variant) GSDR_NO_EXCEPT {
-  if (variant < -4 || variant >= firstCfVariantId() + kNumCfVariants) return -1;
+  if (variant < -4 || variant >= firstWideVariantId() + kNumWideVariants) return -1;
   gForcedVariant.store(variant, std::memory_order_relaxed);
   return 0;
 }
@@ -1086,7 +1130,7 @@ GSDR_C_LINKAGE int gsdrB200HasTuningHooks(void) GSDR_NO_EXCEPT { return 0; }
 #endif
 
 GSDR_C_LINKAGE int gsdrB200NumKernelVariants(void) GSDR_NO_EXCEPT {
-  return firstCfVariantId() + kNumCfVariants;
+  return firstWideVariantId() + kNumWideVariants;
 }
 GSDR_C_LINKAGE int gsdrB200NumPolyphaseVariants(void) GSDR_NO_EXCEPT { return kNumVariants; }
 
@@ -1114,7 +1158,7 @@ GSDR_C_LINKAGE int gsdrB200DescribeKernel(int firType, size_t decimation, size_t
       TcParams tp{};
       const unsigned long long tiles = tcTilesPerChannel(probe, di->maxSmemOptin, &tp);
       if (tiles > 0) {
-        info->variant = firstCfVariantId() + kNumCfVariants;  // == gsdrB200NumKernelVariants(): the tensor-core kernel
+        info->variant = firstWideVariantId() + kNumWideVariants;  // == gsdrB200NumKernelVariants(): the tensor-core kernel
         info->outputsPerThread = 0;
         info->threadsPerBlock = kTcThreads;
         info->phaseGroups = 1;
@@ -1127,6 +1171,20 @@ GSDR_C_LINKAGE int gsdrB200DescribeKernel(int firType, size_t decimation, size_t
     }
 #endif
     TmaGeom tg{};
+    const int wv = chooseWideVariant(probe, di->maxSmemOptin, &tg);
+    if (wv >= 0) {
+      const SpecVariant& ws = kWideVariants[wv];
+      const size_t bout = (size_t)kTmaR * ws.tg;
+      info->variant = firstWideVariantId() + wv;
+      info->outputsPerThread = kTmaR;
+      info->threadsPerBlock = ws.threads();
+      info->phaseGroups = ws.psplit;
+      info->windowBuffers = 2;
+      info->outputsPerBlock = bout;
+      info->sharedBytesPerBlock = tg.smemBytes;
+      info->numBlocks = (numOutputs + bout - 1) / bout;
+      return 0;
+    }
     const int tv = chooseTmaVariant(probe, di->maxSmemOptin, &tg);
     if (tv >= 0) {
       TmaVariant vs;

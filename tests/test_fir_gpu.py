@@ -84,10 +84,10 @@ def test_polyphase_against_oracle(kind, D, T, n_in, cuda_device):
 
 
 # polyphase (cp.async) | TMA-fed | warp-specialised fused NCO | real-input | complex-tap | real x complex-tap variants
-N_POLY, N_TMA, N_SPEC, N_REAL, N_CC, N_ALL = 12, 24, 30, 40, 44, 48
+N_POLY, N_TMA, N_SPEC, N_REAL, N_CC, N_CF, N_ALL = 12, 24, 30, 40, 44, 48, 51  # [N_CF, N_ALL): wide-row kernel (D = 32)
 
 
-@pytest.mark.parametrize("variant", [-2] + list(range(N_ALL)))
+@pytest.mark.parametrize("variant", [-2] + list(range(N_CF)))
 @pytest.mark.parametrize("kind", ["ff", "fc"])
 def test_every_kernel_variant(kind, variant, cuda_device):
     assert (g.num_polyphase_variants(), g.num_kernel_variants()) == (N_POLY, N_ALL)
@@ -160,7 +160,7 @@ def test_complex_tap_kernel(variant, D, T, n_out, cuda_device):
     assert np.abs(y - want).max() <= _tol(taps, x)
 
 
-@pytest.mark.parametrize("variant", [-1] + list(range(N_CC, N_ALL)))
+@pytest.mark.parametrize("variant", [-1] + list(range(N_CC, N_CF)))
 @pytest.mark.parametrize("D,T,n_out", [(1, 63, 50_001), (5, 63, 30_001), (2, 100, 20_000), (4, 127, 9_999),
                                        (8, 255, 8_000), (3, 7, 5_000), (16, 600, 3_001)])
 def test_real_input_complex_tap_kernel(variant, D, T, n_out, cuda_device):
@@ -171,7 +171,7 @@ def test_real_input_complex_tap_kernel(variant, D, T, n_out, cuda_device):
     info = g.describe_kernel(3, D, T, n_out)
     if variant >= 0 and info.variant == -1:
         pytest.skip("variant does not fit this shape")
-    assert N_CC <= info.variant < N_ALL and (variant < 0 or info.variant == variant)
+    assert N_CC <= info.variant < N_CF and (variant < 0 or info.variant == variant)
     dt, dx = torch.from_numpy(taps).to(cuda_device), torch.from_numpy(x).to(cuda_device)
     dy = torch.full((n_out + 4,), 7.0, dtype=torch.complex64, device=cuda_device)
     g.gsdrFirCF(D, dt, T, dx, dy, n_out, 0, None)
@@ -221,6 +221,35 @@ def test_real_input_batched_and_unaligned(cuda_device):
     torch.cuda.synchronize()
     want = oracle.fir("ff", D, taps, xs[0, :n_in], n_out)
     assert np.abs(one.cpu().numpy() - want).max() <= _tol(taps, xs[0])
+
+
+@pytest.mark.parametrize("variant", [-1] + list(range(N_CF, N_ALL)))
+@pytest.mark.parametrize("T,n_in", [(1023, 700_001), (1023, 155_000), (2000, 400_000), (33, 300_000), (1, 200_003)])
+def test_wide_row_kernel_d32(variant, T, n_in, cuda_device):
+    """firTmaWideKernel (segment-pipelined, 512-output tiles): plain FIR and the fused exact NCO, interior tiles (TMA)
+    and the last tile (cp.async, zero fill), against the oracle; variant -1: the automatic choice takes it for
+    captures of at least 296 tiles."""
+    D = 32
+    taps = synth.random_taps(T, 900 + T)
+    x = synth.tone_plus_noise(0, n_in, seed=61)
+    n_out = g.fir_num_outputs(n_in, T, D) - 5
+    g.set_kernel_variant(variant)
+    dt, dx = torch.from_numpy(taps).to(cuda_device), torch.from_numpy(x).to(cuda_device)
+    info = g.describe_kernel(0, D, T, n_out)
+    if variant >= 0:
+        assert info.variant == variant and info.outputsPerBlock == 512
+    y = _run("fc", D, taps, x, n_out, cuda_device)
+    want = oracle.fir("fc", D, taps, x, n_out, threads=8)
+    assert np.abs(y - want).max() <= _tol(taps, x)
+    dz = torch.full((n_out + 8,), float("nan"), dtype=torch.complex64, device=cuda_device)
+    first = 2 ** 36 + 11
+    g.gsdrAdjustFrequencyFirFC(1.0e6, 123456.0, first, D, dt, T, dx, dz[4:], n_out, 0, None)
+    torch.cuda.synchronize()
+    assert torch.isnan(dz[:4].real).all() and torch.isnan(dz[4 + n_out:].real).all()
+    for o0, n_chk in ((0, 1500), (n_out // 2 - 7, 1500), (n_out - 700, 700)):
+        wz = oracle.adjust_frequency_fir_fc(oracle.NCO_EXACT, 1.0e6, 123456.0, first + o0 * D, D, taps, x[o0 * D:], n_chk,
+                                            f64=True)
+        assert np.abs(dz[4 + o0: 4 + o0 + n_chk].cpu().numpy() - wz).max() <= _tol(taps, x)
 
 
 @pytest.mark.parametrize("variant", list(range(N_POLY, N_SPEC)))
