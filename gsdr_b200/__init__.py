@@ -22,7 +22,9 @@ from .api import (  # noqa: F401
     gsdrFirFCInt8,
     gsdrFirFF,
     gsdrFirFFBatched,
+    gsdrAmDemod,
     gsdrFmDemod,
+    gsdrFmDemodFused,
     gsdrFmDemodWorkspace,
     fm_demod_workspace_bytes,
     release_scratch,

@@ -78,6 +78,10 @@ SIGNATURES = {
     "gsdrQuadAmDemod": (cudaError_t, [c_void_p, c_void_p, c_size_t, c_int32, c_void_p]),
     "gsdrFmDemod": (cudaError_t, [c_float, c_float, c_float, c_float, C.c_uint32, c_size_t, c_void_p, c_size_t, c_void_p,
                                   c_void_p, c_size_t, c_int32, c_void_p]),
+    "gsdrAmDemod": (cudaError_t, [c_float, c_float, c_float, C.c_uint32, c_size_t, c_void_p, c_size_t, c_void_p, c_void_p,
+                                  c_size_t, c_int32, c_void_p]),
+    "gsdrFmDemodFused": (cudaError_t, [c_float, c_float, c_float, c_float, C.c_uint32, c_size_t, c_void_p, c_size_t,
+                                       c_void_p, c_void_p, c_size_t, c_int32, c_void_p]),
     "gsdrFmDemodWorkspaceBytes": (c_size_t, [c_size_t]),
     "gsdrFmDemodWorkspace": (cudaError_t, [c_float, c_float, c_float, c_float, C.c_uint32, c_size_t, c_void_p, c_size_t,
                                            c_void_p, c_void_p, c_size_t, c_void_p, c_size_t, c_int32, c_void_p]),

@@ -109,6 +109,20 @@ def gsdrFmDemod(rfSampleRate, tuningFrequency, channelFrequency, frequencyDeviat
                            cudaDevice, _stream(cudaStream)), "gsdrFmDemod")
 
 
+def gsdrAmDemod(rfSampleRate, tuningFrequency, channelFrequency, decimation, firstSampleIndex, lowPassTaps,
+                numLowPassTaps, input, output, numElements, cudaDevice=0, cudaStream=None):
+    _check(L().gsdrAmDemod(rfSampleRate, tuningFrequency, channelFrequency, decimation, firstSampleIndex,
+                           _ptr(lowPassTaps), numLowPassTaps, _ptr(input), _ptr(output), numElements, cudaDevice,
+                           _stream(cudaStream)), "gsdrAmDemod")
+
+
+def gsdrFmDemodFused(rfSampleRate, tuningFrequency, channelFrequency, frequencyDeviation, decimation, firstSampleIndex,
+                     lowPassTaps, numLowPassTaps, input, output, numOutputs, cudaDevice=0, cudaStream=None):
+    _check(L().gsdrFmDemodFused(rfSampleRate, tuningFrequency, channelFrequency, frequencyDeviation, decimation,
+                                firstSampleIndex, _ptr(lowPassTaps), numLowPassTaps, _ptr(input), _ptr(output),
+                                numOutputs, cudaDevice, _stream(cudaStream)), "gsdrFmDemodFused")
+
+
 def gsdrFmDemodWorkspace(rfSampleRate, tuningFrequency, channelFrequency, frequencyDeviation, decimation,
                          firstSampleIndex, lowPassTaps, numLowPassTaps, input, output, numOutputs, workspace,
                          workspaceBytes, cudaDevice=0, cudaStream=None):

@@ -51,6 +51,11 @@ struct TmaParams {
   unsigned tmaRows;      // rows visible to TMA per channel (multiple of 8); windows reaching past it use cp.async
   unsigned y16;
   unsigned dbg;
+  // fused output stage (launch.h: FirEpilogue): 0 = complex outputs, 1 = AM envelope, 2 = FM quadrature demodulation
+  unsigned epi;
+  float epiGain;     // FM: sampleRate / (2 * pi * deviation)
+  unsigned tileOut;  // outputs a tile advances by: 8 * TG, or 8 * TG - 8 for FM (tiles overlap by one row group,
+                     // so every output but a tile's last eight finds its successor inside the tile)
   unsigned long long ncoStep, ncoFirst;
   unsigned ncoFirst32;
   float ncoFs, ncoF;
@@ -141,6 +146,67 @@ __device__ __forceinline__ void tmaLoad4(void* dst, const CUtensorMap* map, unsi
       "[%2];" ::"r"(smemU32(dst)),
       "l"(map), "r"(smemU32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
       : "memory");
+}
+
+// ---- fused output stages ------------------------------------------------------------------------------------
+enum : unsigned { kEpiNone = 0u, kEpiAmEnvelope = 1u, kEpiFmDemod = 2u };
+
+// ref: src/am.cu:49 / src/quad_demod.cu:46-49 — 2 * saturate(|v|) - 1
+__device__ __forceinline__ float amEnvelope(float2 v) { return __fadd_rn(scalbnf(__saturatef(hypotf(v.x, v.y)), 1), -1.0f); }
+
+// gain * arg(next * conj(cur)) with the expression shape nvcc gives the reference's cuCmulf(next, cuConjf(cur)):
+// FMUL, FMUL, FFMA, FFMA (ref: src/quad_demod.cu:30-31; same libdevice atan2f => same bits as the reference kernel)
+__device__ __forceinline__ float quadFmValue(float2 cur, float2 next, float gain) {
+  const float a = __fmul_rn(next.x, cur.y);
+  const float b = __fmul_rn(next.y, cur.y);
+  const float im = __fmaf_rn(next.y, cur.x, -a);
+  const float re = __fmaf_rn(next.x, cur.x, b);
+  return __fmul_rn(gain, atan2f(im, re));
+}
+
+// Complex outputs ob .. ob+7 of one thread -> global memory.
+__device__ __forceinline__ void tmaStoreComplex(const TmaParams& P, unsigned chan, unsigned long long ob,
+                                                const float2 (&acc)[8]) {
+  float2* y = P.y + (size_t)chan * P.yStride;
+  if (P.y16 && ob + 8 <= P.nOut) {
+#pragma unroll
+    for (int r = 0; r < 8; r += 2) {
+      *reinterpret_cast<float4*>(y + ob + r) = make_float4(acc[r].x, acc[r].y, acc[r + 1].x, acc[r + 1].y);
+    }
+  } else {
+#pragma unroll
+    for (int r = 0; r < 8; r++) {
+      if (ob + r < P.nOut) y[ob + r] = acc[r];
+    }
+  }
+}
+
+// Real outputs (AM envelope / FM): values v[0..7] for output indices ob .. ob+7, `count` outputs exist in the channel.
+__device__ __forceinline__ void tmaStoreReal(const TmaParams& P, unsigned chan, unsigned long long ob, const float (&v)[8],
+                                             unsigned long long count) {
+  float* y = reinterpret_cast<float*>(P.y) + (size_t)chan * P.yStride;  // yStride counts floats here
+  if (P.y16 && ob + 8 <= count && (ob & 3ull) == 0) {
+    *reinterpret_cast<float4*>(y + ob) = make_float4(v[0], v[1], v[2], v[3]);
+    *reinterpret_cast<float4*>(y + ob + 4) = make_float4(v[4], v[5], v[6], v[7]);
+  } else {
+#pragma unroll
+    for (int r = 0; r < 8; r++) {
+      if (ob + r < count) y[ob + r] = v[r];
+    }
+  }
+}
+
+// Outputs of thread t of a tile whose first output is o0: complex, or the AM envelope of each.
+__device__ __forceinline__ void tmaStoreTile(const TmaParams& P, unsigned chan, unsigned long long ob,
+                                             const float2 (&acc)[8]) {
+  if (P.epi == kEpiAmEnvelope) {
+    float v[8];
+#pragma unroll
+    for (int r = 0; r < 8; r++) v[r] = amEnvelope(acc[r]);
+    tmaStoreReal(P, chan, ob, v, P.nOut);
+  } else {
+    tmaStoreComplex(P, chan, ob, acc);
+  }
 }
 
 enum TmaBlockKind : int { kBlkPrologue = 0, kBlkSteady = 1, kBlkTail = 2 };
@@ -491,6 +557,7 @@ __global__ void __launch_bounds__(TG* PSPLIT, MINB)
   constexpr unsigned BOUT = kTmaR * TG;
   extern __shared__ __align__(16) unsigned char smemRaw[];
   __shared__ __align__(8) unsigned long long fullBar[2];
+  __shared__ float2 nextFirst[TG];  // FM epilogue: every thread's first output, for its predecessor
   const unsigned D = DT ? (unsigned)DT : P.D;
   const unsigned rowBytes = 8u * D;
   const unsigned segBytes = DT ? tmaSegBytes(DT ? DT : 2) : P.segBytes;
@@ -543,7 +610,7 @@ __global__ void __launch_bounds__(TG* PSPLIT, MINB)
     }
   };
   // A tile is TMA-fed when every row it stages is visible to the tensor map.
-  auto tileIsFast = [&](unsigned tl) -> bool { return tl * BOUT + rowsStaged <= P.tmaRows; };
+  auto tileIsFast = [&](unsigned tl) -> bool { return tl * P.tileOut + rowsStaged <= P.tmaRows; };
   auto issueTile = [&](unsigned c, unsigned tl, unsigned b) {
     if (GSDR_DBG(P) & 1u) return;
     unsigned char* buf = bufBase + b * bufBytes;
@@ -554,12 +621,12 @@ __global__ void __launch_bounds__(TG* PSPLIT, MINB)
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         mbarExpectTx(&fullBar[b], bufBytes);
         for (unsigned sg = 0; sg < numSegs; sg++) {
-          tmaLoad4(buf + sg * 8u * planeBytes, &map, &fullBar[b], (int)(sg * (segBytes / 4u)), (int)(tl * (BOUT / 8)), 0,
+          tmaLoad4(buf + sg * 8u * planeBytes, &map, &fullBar[b], (int)(sg * (segBytes / 4u)), (int)(tl * (P.tileOut / 8)), 0,
                    (int)c);
         }
       }
     } else {
-      tmaStageSlow<NT, DT>(buf, P.x + (size_t)c * P.xStride, (unsigned long long)tl * BOUT * D, rowsStaged, planeBytes, P);
+      tmaStageSlow<NT, DT>(buf, P.x + (size_t)c * P.xStride, (unsigned long long)tl * P.tileOut * D, rowsStaged, planeBytes, P);
     }
   };
 
@@ -573,7 +640,7 @@ __global__ void __launch_bounds__(TG* PSPLIT, MINB)
   for (unsigned it = 0; chan < P.numChannels; it++) {
     const unsigned b = (NBUF == 2) ? (it & 1u) : 0u;
     unsigned char* buf = bufBase + b * bufBytes;
-    const unsigned long long o0 = (unsigned long long)tile * BOUT;
+    const unsigned long long o0 = (unsigned long long)tile * P.tileOut;
     unsigned nextChan = chan, nextTile = tile;
     advance(nextChan, nextTile);
     if (NBUF == 2) {
@@ -650,19 +717,21 @@ __global__ void __launch_bounds__(TG* PSPLIT, MINB)
         }
       }
       const unsigned long long ob = o0 + (unsigned long long)t * kTmaR;
-      float2* y = P.y + (size_t)chan * P.yStride;
       if (GSDR_DBG(P) & 4u) {
-        if (acc[0].x == 123.456f) y[0] = acc[1];  // measurement hook: no output traffic
-      } else if (P.y16 && ob + kTmaR <= P.nOut) {
+        if (acc[0].x == 123.456f) P.y[(size_t)chan * P.yStride] = acc[1];  // measurement hook: no output traffic
+      } else if (P.epi == kEpiFmDemod) {
+        // d[n] = gain * arg(y[n+1] * conj(y[n])) (ref: src/quad_demod.cu:23-37, src/fm.cu:58-68): the successor of this
+        // thread's last output is the next thread's first one; the tile's last thread only supplies it (its own
+        // outputs belong to the next tile, which starts 8 outputs before this one ends)
+        nextFirst[t] = acc[0];
+        asm volatile("bar.sync 3, %0;" ::"n"(TG) : "memory");
+        const float2 nx = (t + 1 < (unsigned)TG) ? nextFirst[t + 1] : make_float2(0.0f, 0.0f);
+        float v[8];
 #pragma unroll
-        for (int r = 0; r < kTmaR; r += 2) {
-          *reinterpret_cast<float4*>(y + ob + r) = make_float4(acc[r].x, acc[r].y, acc[r + 1].x, acc[r + 1].y);
-        }
+        for (int r = 0; r < 8; r++) v[r] = quadFmValue(acc[r], r < 7 ? acc[r + 1] : nx, P.epiGain);
+        if (t + 1 < (unsigned)TG) tmaStoreReal(P, chan, ob, v, P.nOut - 1);  // nOut low-pass values, nOut - 1 phase steps
       } else {
-#pragma unroll
-        for (int r = 0; r < kTmaR; r++) {
-          if (ob + r < P.nOut) y[ob + r] = acc[r];
-        }
+        tmaStoreTile(P, chan, ob, acc);
       }
     }
     chan = nextChan;
@@ -811,19 +880,7 @@ __global__ void __launch_bounds__(TG* PSPLIT + 32 * MIXW, MINB)
       }
     }
     if (grp == 0) {
-      const unsigned long long ob = o0 + (unsigned long long)t * kTmaR;
-      float2* y = P.y + (size_t)chan * P.yStride;
-      if (P.y16 && ob + kTmaR <= P.nOut) {
-#pragma unroll
-        for (int r = 0; r < kTmaR; r += 2) {
-          *reinterpret_cast<float4*>(y + ob + r) = make_float4(acc[r].x, acc[r].y, acc[r + 1].x, acc[r + 1].y);
-        }
-      } else {
-#pragma unroll
-        for (int r = 0; r < kTmaR; r++) {
-          if (ob + r < P.nOut) y[ob + r] = acc[r];
-        }
-      }
+      tmaStoreTile(P, chan, o0 + (unsigned long long)t * kTmaR, acc);
     }
   }
 }
@@ -1776,19 +1833,7 @@ __global__ void __launch_bounds__(TG* PSPLIT + 32 * MIXW, MINB)
       mbarArrive(&emptyBar[lastB]);  // the buffer may now be refilled
     }
     if (grp == 0) {
-      const unsigned long long ob = o0 + (unsigned long long)t * kTmaR;
-      float2* y = P.y + (size_t)chan * P.yStride;
-      if (P.y16 && ob + kTmaR <= P.nOut) {
-#pragma unroll
-        for (int r = 0; r < kTmaR; r += 2) {
-          *reinterpret_cast<float4*>(y + ob + r) = make_float4(acc[r].x, acc[r].y, acc[r + 1].x, acc[r + 1].y);
-        }
-      } else {
-#pragma unroll
-        for (int r = 0; r < kTmaR; r++) {
-          if (ob + r < P.nOut) y[ob + r] = acc[r];
-        }
-      }
+      tmaStoreTile(P, chan, o0 + (unsigned long long)t * kTmaR, acc);
     }
   }
 }

@@ -337,7 +337,9 @@ static int chooseTmaVariant(const FirCall& c, int maxSmem, TmaGeom* geom) noexce
   // single-buffered kernel then matches (D = 10: 0.262 vs 0.263 ms) or beats (D = 6: 0.411 vs 0.478 ms, 255 taps,
   // 2^26 samples) the warp-specialised one
   const bool oddPairCount = c.decimation <= 16 && ((c.decimation / 2) % 2 == 1);
-  if (c.nco == kNcoExact && !oddPairCount) {
+  // (D = 4: two branch pairs cannot keep two filter groups busy: 64 x 1 single-buffered 0.268 ms against 0.410 ms for
+  //  the warp-specialised kernel, 127 taps, 2^26 samples: profiles/r02/sweep_nco_d4.jsonl)
+  if (c.nco == kNcoExact && !oddPairCount && c.decimation >= 8 && c.epilogue != kFirEpiFmDemod) {
     // fused NCO: copy + mix on dedicated warps, overlapped with the FIR of the previous tile
     // (tools/sweep.py --nco: 64 x 2 filter threads + 4 mixer warps for narrow rows, 32 x 4 + 4 for wide rows)
     const int sid = kNumTmaVariants + (c.decimation > 16 ? 1 : 2);
@@ -389,7 +391,7 @@ static bool wideGeometry(const SpecVariant& v, size_t D, size_t T, bool nco, Tma
 
 // Returns the wide-row variant for this call, or -1 when the call does not qualify.
 static int chooseWideVariant(const FirCall& c, int maxSmem, TmaGeom* geom) noexcept {
-  if (c.type != kFirFC || c.nco == kNcoLiteral) return -1;
+  if (c.type != kFirFC || c.nco == kNcoLiteral || c.epilogue == kFirEpiFmDemod) return -1;
   if (c.numOutputs >= 0xfff00000ull || c.decimation != 32 || !encodeTiled()) return -1;
   if ((uintptr_t)c.input % 16 != 0) return -1;
   if (c.numChannels > 1 && ((c.inputStride % 2) != 0 || c.tapStride != 0)) return -1;
@@ -472,11 +474,16 @@ static cudaError_t launchTma(const FirCall& c, int variant, const TmaGeom& geom,
     return cudaErrorInvalidValue;
   }
   const size_t bout = (size_t)kTmaR * v.tg;
-  const unsigned long long tiles = (c.numOutputs + bout - 1) / bout;
+  const bool fm = c.epilogue == kFirEpiFmDemod;
+  if (fm && (wideVariant >= 0 || ccVariant >= 0 || mixw > 0)) return cudaErrorNotSupported;
+  // FM: numOutputs phase steps need numOutputs + 1 low-pass values; tiles overlap by their last row group
+  const size_t firOutputs = c.numOutputs + (fm ? 1 : 0);
+  const size_t tileOut = fm ? bout - kTmaR : bout;
+  const unsigned long long tiles = (c.numOutputs + tileOut - 1) / tileOut;
   const unsigned long long total = tiles * c.numChannels;
   if (tiles > 0x7fffffffull || total > 0x7fffffffull) return cudaErrorInvalidValue;
   const size_t D = c.decimation;
-  const unsigned long long nIn = (unsigned long long)(c.numOutputs - 1) * D + c.tapCount;
+  const unsigned long long nIn = (unsigned long long)(firOutputs - 1) * D + c.tapCount;
   const unsigned long long tmaRows = (nIn / (8 * D)) * 8;  // complete groups of 8 rows only: TMA never reads past nIn
   if (tmaRows / 8 > 0xffffffffull) return cudaErrorInvalidValue;
 
@@ -484,8 +491,11 @@ static cudaError_t launchTma(const FirCall& c, int variant, const TmaGeom& geom,
   P.x = (const float2*)c.input;
   P.h = (const float*)c.taps;
   P.y = (float2*)c.output;
-  P.nOut = c.numOutputs;
+  P.nOut = firOutputs;
   P.nIn = nIn;
+  P.epi = (unsigned)c.epilogue;
+  P.epiGain = c.epilogueGain;
+  P.tileOut = (unsigned)tileOut;
   P.xStride = c.inputStride;
   P.yStride = c.outputStride;
   P.hStride = c.tapStride;
@@ -502,7 +512,10 @@ static cudaError_t launchTma(const FirCall& c, int variant, const TmaGeom& geom,
   P.swzShift = geom.swzShift;
   P.swzMask = geom.swzMask;
   P.tmaRows = (unsigned)(tmaRows > 0xffffffffull ? 0xffffffffull : tmaRows);
-  P.y16 = ((uintptr_t)c.output % 16 == 0 && (c.numChannels == 1 || (c.outputStride * 8) % 16 == 0)) ? 1u : 0u;
+  {
+    const size_t oe = c.epilogue == kFirEpiNone ? 8 : 4;  // real outputs with a fused stage
+    P.y16 = ((uintptr_t)c.output % 16 == 0 && (c.numChannels == 1 || (c.outputStride * oe) % 16 == 0)) ? 1u : 0u;
+  }
   P.dbg = debugFlags();
   P.ncoStep = ncoPhaseStep(c.frequencyShift, c.sampleRate);
   P.ncoFirst = c.firstSampleIndex;
@@ -766,7 +779,7 @@ static unsigned long long tcTilesPerChannel(const FirCall& c, int maxSmem, TcPar
   if (c.type != kFirFC || c.nco != kNcoNone) return 0;
   // Measured and NOT adopted (profiles/r02_tc_*): 0.224 ms against the FFMA2 kernel's 0.166 ms on
   // BASELINE config 2.  The kernel stays reachable through the tuning build's override only.
-  if (forcedVariant() != kForceTensorCore) return 0;
+  if (forcedVariant() != kForceTensorCore || c.epilogue != kFirEpiNone) return 0;
   const size_t D = c.decimation, T = c.tapCount;
   if (D != 4 && D != 8 && D != 16) return 0;
   const size_t SD = (size_t)kTcS * D;
@@ -803,6 +816,7 @@ cudaError_t enqueueFir(const FirCall& c, cudaStream_t stream) noexcept {
   if (c.numOutputs == 0 || c.numChannels == 0) return cudaSuccess;
   if (c.decimation == 0) return cudaErrorInvalidValue;
   if (c.nco != kNcoNone && c.type != kFirFC) return cudaErrorInvalidValue;
+  if (c.epilogue != kFirEpiNone && (c.type != kFirFC || c.tapCount == 0)) return cudaErrorNotSupported;
   if (c.tapCount == 0) {
     // the reference writes zero<OUT_T>() when the tap loop does not run (ref: src/fir.cu:67-70)
     for (size_t ch = 0; ch < c.numChannels; ch++) {
@@ -831,6 +845,7 @@ cudaError_t enqueueFir(const FirCall& c, cudaStream_t stream) noexcept {
     if (wv >= 0) return launchTma(c, -1, tg, dev, info->smCount, stream, -1, wv);
     const int tv = chooseTmaVariant(c, info->maxSmemOptin, &tg);
     if (tv >= 0) return launchTma(c, tv, tg, dev, info->smCount, stream);
+    if (c.epilogue != kFirEpiNone) return cudaErrorNotSupported;  // only the TMA-fed kernels have fused output stages
     RealGeom rg{};
     const int rv = chooseRealVariant(c, info->maxSmemOptin, &rg);
     if (rv >= 0) return launchReal(c, rv, rg, dev, info->smCount, stream);

@@ -10,6 +10,10 @@ namespace gsdr_b200 {
 
 enum FirType : int { kFirFC = 0, kFirFF = 1, kFirCC = 2, kFirCF = 3 };
 enum NcoMode : int { kNcoNone = 0, kNcoExact = 1, kNcoLiteral = 2 };
+// Output stage fused into the FIR's store path (FC only): the complex outputs themselves, their AM envelope
+// 2 * sat(|y|) - 1 (ref: src/am.cu:49), or the FM quadrature demodulation gain * arg(y[n+1] * conj(y[n]))
+// (ref: src/quad_demod.cu:23-37).  With kFirEpiFmDemod, numOutputs counts demodulated values: the FIR produces one more.
+enum FirEpilogue : int { kFirEpiNone = 0, kFirEpiAmEnvelope = 1, kFirEpiFmDemod = 2 };
 
 struct FirCall {
   FirType type = kFirFC;
@@ -26,9 +30,14 @@ struct FirCall {
   // NCO
   float sampleRate = 0.0f, frequencyShift = 0.0f;
   size_t firstSampleIndex = 0;
+  // fused output stage: `output` is then a float array (strides in floats)
+  FirEpilogue epilogue = kFirEpiNone;
+  float epilogueGain = 0.0f;
 };
 
 // Enqueue on `stream` of the CURRENT device (callers switch devices). No sync, no allocation.
+// A call with a fused output stage returns cudaErrorNotSupported (nothing enqueued) when the kernel that fits its shape
+// has no such stage; the caller then runs the stage as a separate kernel.
 cudaError_t enqueueFir(const FirCall& call, cudaStream_t stream) noexcept;
 
 // int8 IQ input (<gsdr/conversion.h>): conversion fused into the staging, optional exact NCO.  Same conventions.

@@ -69,6 +69,27 @@ GSDR_C_LINKAGE GSDR_PUBLIC cudaError_t gsdrFmDemodWorkspace(
     int32_t cudaDevice,
     cudaStream_t cudaStream) GSDR_NO_EXCEPT;
 /*
+ * Additive: the stage as ONE kernel — the quadrature demodulator runs in the FIR's store path, the low-pass values
+ * never reach HBM and nothing is allocated.  Measured 4.5 % SLOWER than gsdrFmDemod on BASELINE config 5 (the
+ * arctangent costs the issue-bound FIR kernel more than the separate launch costs), hence not the default.  Returns
+ * cudaErrorNotSupported, with nothing enqueued, for shapes outside the TMA-fed kernels (odd decimations, unaligned
+ * input, tap sets beyond shared memory): use gsdrFmDemod / gsdrFmDemodWorkspace there.
+ */
+GSDR_C_LINKAGE GSDR_PUBLIC cudaError_t gsdrFmDemodFused(
+    float rfSampleRate,
+    float tuningFrequency,
+    float channelFrequency,
+    float frequencyDeviation,
+    uint32_t decimation,
+    size_t firstSampleIndex,
+    const float* lowPassTaps,
+    size_t numLowPassTaps,
+    const cuComplex* input,
+    float* output,
+    size_t numOutputs,
+    int32_t cudaDevice,
+    cudaStream_t cudaStream) GSDR_NO_EXCEPT;
+/*
  * Returns the memory gsdrFmDemod's private scratch pool on cudaDevice is holding to the driver (blocks still in use by
  * enqueued work are kept).  A long-running receiver calls this after its largest block size shrinks; never required.
  */

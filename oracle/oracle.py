@@ -133,6 +133,13 @@ def quad_fm_demod(x, gain: float, num_out: int | None = None):
     return out
 
 
+def quad_am_demod(x):
+    """2 * saturate(|x|) - 1 per sample in float32 (ref: src/quad_demod.cu:46-49, src/am.cu:49)."""
+    x = np.ascontiguousarray(x, dtype=np.complex64)
+    mag = np.hypot(x.real.astype(np.float32), x.imag.astype(np.float32)).astype(np.float32)
+    return (np.float32(2.0) * np.clip(mag, np.float32(0.0), np.float32(1.0)) - np.float32(1.0)).astype(np.float32)
+
+
 # ---- pure-numpy second opinion (tiny cases only) -----------------------------------------------------------
 
 def fir_numpy_f64(decimation: int, taps, x, num_out: int | None = None):

@@ -103,3 +103,72 @@ def test_fm_chain_config5_shape_small(cuda_device):
     o_dm = oracle.quad_fm_demod(o_lp, gain, n2)
     o_au = oracle.fir("ff", D3, h3, o_dm, n3)
     assert np.abs(au.cpu().numpy() - o_au).max() <= gain * 6e-5 * float(np.abs(h3).sum())
+
+
+# ---- fused output stages: quad demod / AM envelope in the FIR's store path -----------------
+
+@pytest.mark.parametrize("D,T,n_out", [(10, 255, 300_001), (8, 255, 100_000), (4, 127, 65_537), (32, 1023, 160_000),
+                                       (6, 100, 50_000), (16, 500, 40_003), (10, 255, 7)])
+def test_am_demod_against_oracle_chain(D, T, n_out, cuda_device):
+    """gsdrAmDemod (ref: include/gsdr/am.h:25-37, src/am.cu:41-49) == oracle(mix + FIR) -> 2*sat(|y|) - 1."""
+    fs, tuning, channel, first = 2.4e6, 100.0e6, 100.3e6, 2 ** 34 + 5
+    n_in = g.fir_num_inputs(n_out, T, D)
+    x = (1.6 * synth.tone_plus_noise(0, n_in, seed=80 + D, tone_cycles_per_sample=0.125)).astype(np.complex64)
+    taps = synth.lowpass_taps(T, D, cutoff=0.45)
+    dx, dt = torch.from_numpy(x).to(cuda_device), torch.from_numpy(taps).to(cuda_device)
+    dy = torch.full((n_out + 8,), float("nan"), dtype=torch.float32, device=cuda_device)
+    g.gsdrAmDemod(fs, tuning, channel, D, first, dt, T, dx, dy[4:], n_out, 0, None)
+    torch.cuda.synchronize()
+    y = dy.cpu().numpy()
+    assert np.isnan(y[:4]).all() and np.isnan(y[4 + n_out:]).all()
+    n_chk = min(n_out, 4000)
+    for o0 in sorted({0, (n_out - n_chk) // 2, n_out - n_chk}):
+        lp = oracle.adjust_frequency_fir_fc(oracle.NCO_EXACT, fs, tuning - channel, first + o0 * D, D, taps,
+                                            x[o0 * D:], n_chk)
+        want = oracle.quad_am_demod(lp)
+        tol = 2.0 * 1e-5 * float(np.abs(taps).sum()) * float(np.abs(x).max()) + 5e-7
+        assert np.abs(y[4 + o0: 4 + o0 + n_chk] - want).max() <= tol
+    assert y[4:4 + n_out].min() >= -1.0 and y[4:4 + n_out].max() <= 1.0
+    # the unfused path (direct kernel: no fused stage, pool scratch + envelope kernel) gives the same within tolerance
+    g.set_kernel_variant(-2)
+    dz = torch.zeros(n_out, dtype=torch.float32, device=cuda_device)
+    g.gsdrAmDemod(fs, tuning, channel, D, first, dt, T, dx, dz, min(n_out, 20_000), 0, None)
+    torch.cuda.synchronize()
+    m = min(n_out, 20_000)
+    assert np.abs(dz[:m].cpu().numpy() - y[4:4 + m]).max() <= 2.0 * 1e-5 * float(np.abs(taps).sum()) * float(np.abs(x).max()) + 5e-7
+
+
+@pytest.mark.parametrize("D,T,n_out", [(10, 255, 300_001), (8, 255, 100_003), (4, 127, 70_000), (32, 1023, 50_000),
+                                       (6, 100, 20_001), (10, 255, 1), (10, 255, 503), (10, 255, 504), (10, 255, 505)])
+def test_fm_demod_fused_stage_equals_unfused_chain(D, T, n_out, cuda_device):
+    """The quadrature demodulator in the FIR's store path (tiles overlap by one row group) against the two-kernel
+    chain composed from the C-ABI calls: phase steps agree to the FIR tolerance, tile seams included."""
+    fs, tuning, channel, dev_hz, first = 2.4e6, 100.0e6, 100.3e6, 75e3, 2 ** 33 + 77
+    n_in = n_out * D + T
+    x = _fm_signal(n_in, fs, dev_hz, 1000.0, channel - tuning, seed=85)
+    taps = synth.lowpass_taps(T, D, cutoff=0.45)
+    dx, dt = torch.from_numpy(x).to(cuda_device), torch.from_numpy(taps).to(cuda_device)
+    dy = torch.full((n_out + 8,), float("nan"), dtype=torch.float32, device=cuda_device)
+    g.gsdrFmDemodFused(fs, tuning, channel, dev_hz, D, first, dt, T, dx, dy[4:], n_out, 0, None)
+    lp = torch.zeros(n_out + 1, dtype=torch.complex64, device=cuda_device)
+    dm = torch.zeros(n_out, dtype=torch.float32, device=cuda_device)
+    g.gsdrAdjustFrequencyFirFC(fs, tuning - channel, first, D, dt, T, dx, lp, n_out + 1, 0, None)
+    gain = fs / (2 * math.pi * dev_hz)
+    g.gsdrQuadFmDemod(lp, dm, gain, n_out, 0, None)
+    torch.cuda.synchronize()
+    y = dy.cpu().numpy()
+    assert np.isnan(y[:4]).all() and np.isnan(y[4 + n_out:]).all()
+    assert np.abs(y[4:4 + n_out] - dm.cpu().numpy()).max() <= gain * 6e-5
+
+
+def test_fm_demod_fused_reports_unsupported_shapes(cuda_device):
+    D, T, n_out = 5, 63, 1000  # odd decimation: no TMA-fed kernel, hence no fused stage
+    x = synth.tone_plus_noise(0, n_out * D + T, seed=86, device=cuda_device)
+    dt = torch.from_numpy(synth.lowpass_taps(T, D)).to(cuda_device)
+    dy = torch.zeros(n_out, dtype=torch.float32, device=cuda_device)
+    with pytest.raises(g.CudaError) as e:
+        g.gsdrFmDemodFused(2.4e6, 100.0e6, 100.3e6, 75e3, D, 0, dt, T, x, dy, n_out, 0, None)
+    assert e.value.code == 801  # cudaErrorNotSupported
+    g.gsdrFmDemod(2.4e6, 100.0e6, 100.3e6, 75e3, D, 0, dt, T, x, dy, n_out, 0, None)  # the default form serves it
+    torch.cuda.synchronize()
+    assert float(dy.abs().max()) > 0.0
