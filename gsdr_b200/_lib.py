@@ -73,6 +73,8 @@ SIGNATURES = {
     "gsdrAdjustFrequencyFirFC": (cudaError_t, _NCO_ARGS),
     "gsdrAdjustFrequencyFirFCLiteral": (cudaError_t, _NCO_ARGS),
     "gsdrNcoPhaseStep": (C.c_uint64, [c_float, c_float]),
+    "gsdrChannelizeFC": (cudaError_t, [c_float, C.POINTER(c_float), c_size_t, c_size_t, c_size_t, c_void_p, c_size_t,
+                                       c_void_p, c_void_p, c_size_t, c_size_t, c_int32, c_void_p]),
     # include/gsdr/quad_demod.h, include/gsdr/fm.h
     "gsdrQuadFmDemod": (cudaError_t, [c_void_p, c_void_p, c_float, c_size_t, c_int32, c_void_p]),
     "gsdrQuadAmDemod": (cudaError_t, [c_void_p, c_void_p, c_size_t, c_int32, c_void_p]),

@@ -83,6 +83,15 @@ gsdrAdjustFrequencyFirFC = _nco("gsdrAdjustFrequencyFirFC")
 gsdrAdjustFrequencyFirFCLiteral = _nco("gsdrAdjustFrequencyFirFCLiteral")
 
 
+def gsdrChannelizeFC(sampleRate, frequencyShifts, firstSampleIndex, decimation, taps, tapCount, input, output,
+                     outputStride, numOutputs, cudaDevice=0, cudaStream=None):
+    """One input, len(frequencyShifts) channels: output[k * outputStride + n] (frequencyShifts: host floats)."""
+    shifts = (C.c_float * len(frequencyShifts))(*[float(f) for f in frequencyShifts])
+    _check(L().gsdrChannelizeFC(sampleRate, shifts, len(frequencyShifts), firstSampleIndex, decimation, _ptr(taps),
+                                tapCount, _ptr(input), _ptr(output), outputStride, numOutputs, cudaDevice,
+                                _stream(cudaStream)), "gsdrChannelizeFC")
+
+
 gsdrFirFCInt8 = _fir("gsdrFirFCInt8")
 gsdrAdjustFrequencyFirFCInt8 = _nco("gsdrAdjustFrequencyFirFCInt8")
 

@@ -15,6 +15,25 @@ namespace gsdr_b200 {
 // one stderr line on failure, clears the runtime's last-error slot (defined in gsdr_fir.cu)
 cudaError_t report(cudaError_t st, const char* what) noexcept;
 
+// The occupancy answer for a (kernel instantiation, device, dynamic shared memory) triple never changes: cache the last
+// one per launch site and device (one query per call was ~10 % of the host-side cost of a call).
+struct OccCache {
+  std::atomic<unsigned long long> entry[64];  // (smem << 8) | CTAs per SM, 0 = empty
+};
+template <class K>
+static cudaError_t occupancyCached(OccCache& cache, K kernel, int threads, size_t smem, int dev, int* perSm) noexcept {
+  const unsigned long long e = cache.entry[dev & 63].load(std::memory_order_acquire);
+  if (e != 0 && (e >> 8) == (unsigned long long)smem) {
+    *perSm = (int)(e & 0xffu);
+    return cudaSuccess;
+  }
+  const cudaError_t st = cudaOccupancyMaxActiveBlocksPerMultiprocessor(perSm, kernel, threads, smem);
+  if (st == cudaSuccess && *perSm > 0 && *perSm < 256) {
+    cache.entry[dev & 63].store(((unsigned long long)smem << 8) | (unsigned)*perSm, std::memory_order_release);
+  }
+  return st;
+}
+
 struct TmaVariant {
   int tg, psplit, nbuf, minBlocks;
   int threads() const { return tg * psplit; }
@@ -129,7 +148,8 @@ static cudaError_t launchTmaT(const CUtensorMap& map, TmaParams& P, size_t smem,
     configured[dev & 63].store(smem, std::memory_order_release);
   }
   int perSm = 0;
-  cudaError_t st = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, kernel, TG * PSPLIT, smem);
+  static OccCache occ;
+  cudaError_t st = occupancyCached(occ, kernel, TG * PSPLIT, smem, dev, &perSm);
   if (st != cudaSuccess) return report(st, "cudaOccupancyMaxActiveBlocksPerMultiprocessor");
   if (perSm < 1) return cudaErrorInvalidConfiguration;
   // Warps are pinned to one of the SM's four sub-partitions; with a static tile assignment the kernel runs at the
@@ -181,7 +201,8 @@ static cudaError_t launchSpecT(const CUtensorMap& map, TmaParams& P, size_t smem
     configured[dev & 63].store(smem, std::memory_order_release);
   }
   int perSm = 0;
-  cudaError_t st = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, kernel, kThreads, smem);
+  static OccCache occ;
+  cudaError_t st = occupancyCached(occ, kernel, kThreads, smem, dev, &perSm);
   if (st != cudaSuccess) return report(st, "cudaOccupancyMaxActiveBlocksPerMultiprocessor");
   if (perSm < 1) return cudaErrorInvalidConfiguration;
   {
@@ -231,6 +252,33 @@ static cudaError_t launchWideD(int mode, int variant, const CUtensorMap& map, Tm
   }
 }
 
+template <int TG, int PSPLIT, int DT, int MINB>
+static cudaError_t launchChanT(const CUtensorMap& map, ChanParams& P, size_t smem, int dev, int smCount,
+                               cudaStream_t stream) noexcept {
+  static std::atomic<size_t> configured[64];
+  auto kernel = firTmaChannelizerKernel<TG, PSPLIT, DT, MINB>;
+  if (smem > configured[dev & 63].load(std::memory_order_acquire)) {
+    cudaError_t st = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (st != cudaSuccess) return report(st, "cudaFuncSetAttribute(MaxDynamicSharedMemorySize)");
+    configured[dev & 63].store(smem, std::memory_order_release);
+  }
+  int perSm = 0;
+  static OccCache occ;
+  cudaError_t st = occupancyCached(occ, kernel, TG * PSPLIT, smem, dev, &perSm);
+  if (st != cudaSuccess) return report(st, "cudaOccupancyMaxActiveBlocksPerMultiprocessor");
+  if (perSm < 1) return cudaErrorInvalidConfiguration;
+  {
+    const int warpsPerCta = (TG * PSPLIT) / 32;
+    int balanced = perSm;
+    while (balanced > 1 && (balanced * warpsPerCta) % 4 != 0) balanced--;
+    if ((balanced * warpsPerCta) % 4 == 0) perSm = balanced;
+  }
+  const unsigned long long resident = (unsigned long long)perSm * (unsigned)smCount;
+  const unsigned grid = (unsigned)(P.tilesPerChannel < resident ? P.tilesPerChannel : resident);
+  void* args[] = {(void*)&map, (void*)&P};
+  return cudaLaunchKernel((const void*)kernel, dim3(grid), dim3(TG * PSPLIT), args, smem, stream);
+}
+
 template <int DT>
 static cudaError_t launchSpecD(int variant, const CUtensorMap& map, TmaParams& P, size_t smem, int dev, int smCount,
                                cudaStream_t stream) noexcept {
@@ -266,7 +314,8 @@ static cudaError_t launchCcT(const CUtensorMap& map, TmaParams& P, size_t smem, 
     configured[dev & 63].store(smem, std::memory_order_release);
   }
   int perSm = 0;
-  cudaError_t st = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, kernel, TG * PSPLIT, smem);
+  static OccCache occ;
+  cudaError_t st = occupancyCached(occ, kernel, TG * PSPLIT, smem, dev, &perSm);
   if (st != cudaSuccess) return report(st, "cudaOccupancyMaxActiveBlocksPerMultiprocessor");
   if (perSm < 1) return cudaErrorInvalidConfiguration;
   {
@@ -306,7 +355,8 @@ static cudaError_t launchRealT(RealParams& P, size_t smem, int dev, int smCount,
     configured[dev & 63].store(smem, std::memory_order_release);
   }
   int perSm = 0;
-  cudaError_t st = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, kernel, kThreads, smem);
+  static OccCache occ;
+  cudaError_t st = occupancyCached(occ, kernel, kThreads, smem, dev, &perSm);
   if (st != cudaSuccess) return report(st, "cudaOccupancyMaxActiveBlocksPerMultiprocessor");
   if (perSm < 1) return cudaErrorInvalidConfiguration;
   {
@@ -386,7 +436,8 @@ static cudaError_t launchInt8T(Int8Params& P, size_t smem, int dev, int smCount,
     configured[dev & 63].store(smem, std::memory_order_release);
   }
   int perSm = 0;
-  cudaError_t st = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, kernel, kThreads, smem);
+  static OccCache occ;
+  cudaError_t st = occupancyCached(occ, kernel, kThreads, smem, dev, &perSm);
   if (st != cudaSuccess) return report(st, "cudaOccupancyMaxActiveBlocksPerMultiprocessor");
   if (perSm < 1) return cudaErrorInvalidConfiguration;
   {
@@ -422,6 +473,13 @@ static cudaError_t launchInt8D(int variant, Int8Params& P, size_t smem, int dev,
 #define GSDR_DECLARE_TMA_DT(DT) cudaError_t launchTmaDt##DT(int mode, int variant, GSDR_TMA_ARGS) noexcept;
 #define GSDR_DECLARE_SPEC_DT(DT) cudaError_t launchSpecDt##DT(int variant, GSDR_TMA_ARGS) noexcept;
 #define GSDR_DECLARE_CC_DT(DT) cudaError_t launchCcDt##DT(int variant, GSDR_TMA_ARGS) noexcept;
+// K-shift channeliser (firTmaChannelizerKernel): one tile shape per compile-time decimation
+struct ChanShape {
+  int D, tg, psplit;
+};
+static constexpr ChanShape kChanShapes[] = {{4, 64, 1}, {8, 32, 2}, {10, 64, 1}};
+cudaError_t launchChan(int D, const CUtensorMap& map, ChanParams& P, size_t smem, int dev, int smCount,
+                       cudaStream_t stream) noexcept;
 #define GSDR_DECLARE_WIDE_DT(DT) cudaError_t launchWideDt##DT(int mode, int variant, GSDR_TMA_ARGS) noexcept;
 #define GSDR_DEFINE_WIDE_DT(DT)                                                  \
   cudaError_t launchWideDt##DT(int mode, int variant, GSDR_TMA_ARGS) noexcept {  \

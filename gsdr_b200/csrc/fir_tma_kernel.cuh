@@ -345,7 +345,7 @@ struct MixStatic {
 template <int NT, int DT>
 __device__ __forceinline__ void tmaMixRowsStatic(unsigned char* buf, unsigned mhCount, unsigned planeBytes,
                                                  const float2* ncoA, const float2* ncoR, const TmaParams& P,
-                                                 unsigned lt) {
+                                                 unsigned lt, int dstDelta = 0) {  // dstDelta: mixed window goes to buf + dstDelta
   using M = MixStatic<NT, DT>;
   constexpr unsigned CH = M::CH, CHUNKS = M::CHUNKS, G = M::G;
   constexpr unsigned SEG = tmaSegBytes(DT ? DT : 2);
@@ -385,7 +385,7 @@ __device__ __forceinline__ void tmaMixRowsStatic(unsigned char* buf, unsigned mh
         const float2 w1 = cmulf(an, r[2 * j + 1]);
         const float2 a = cmulf(make_float2(x[j].x, x[j].y), w0);
         const float2 c = cmulf(make_float2(x[j].z, x[j].w), w1);
-        *reinterpret_cast<float4*>(row + off[j]) = make_float4(a.x, a.y, c.x, c.y);
+        *reinterpret_cast<float4*>(row + off[j] + dstDelta) = make_float4(a.x, a.y, c.x, c.y);
       }
     }
   }
@@ -557,7 +557,9 @@ __global__ void __launch_bounds__(TG* PSPLIT, MINB)
   constexpr unsigned BOUT = kTmaR * TG;
   extern __shared__ __align__(16) unsigned char smemRaw[];
   __shared__ __align__(8) unsigned long long fullBar[2];
-  __shared__ float2 nextFirst[TG];  // FM epilogue: every thread's first output, for its predecessor
+  // fused output stages exist in the NCO modes only (gsdrAmDemod / gsdrFmDemodFused): the plain FIR keeps its schedule
+  constexpr bool kHasEpilogue = MODE != kPolyFC;
+  __shared__ float2 nextFirst[kHasEpilogue ? TG : 1];  // FM: every thread's first output, for its predecessor
   const unsigned D = DT ? (unsigned)DT : P.D;
   const unsigned rowBytes = 8u * D;
   const unsigned segBytes = DT ? tmaSegBytes(DT ? DT : 2) : P.segBytes;
@@ -579,6 +581,7 @@ __global__ void __launch_bounds__(TG* PSPLIT, MINB)
   const unsigned ppBegin = (grp * numPairs) / PSPLIT;
   const unsigned ppEnd = ((grp + 1) * numPairs) / PSPLIT;
   const unsigned rowsStaged = BOUT + P.Jpad;  // rows a tile needs (8 per output block + the taps' reach)
+  const unsigned tileOut = kHasEpilogue ? P.tileOut : BOUT;  // FM tiles overlap by one row group
 
   if (tid == 0) {
     mbarInit(&fullBar[0], 1);
@@ -610,7 +613,7 @@ __global__ void __launch_bounds__(TG* PSPLIT, MINB)
     }
   };
   // A tile is TMA-fed when every row it stages is visible to the tensor map.
-  auto tileIsFast = [&](unsigned tl) -> bool { return tl * P.tileOut + rowsStaged <= P.tmaRows; };
+  auto tileIsFast = [&](unsigned tl) -> bool { return tl * tileOut + rowsStaged <= P.tmaRows; };
   auto issueTile = [&](unsigned c, unsigned tl, unsigned b) {
     if (GSDR_DBG(P) & 1u) return;
     unsigned char* buf = bufBase + b * bufBytes;
@@ -621,12 +624,12 @@ __global__ void __launch_bounds__(TG* PSPLIT, MINB)
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         mbarExpectTx(&fullBar[b], bufBytes);
         for (unsigned sg = 0; sg < numSegs; sg++) {
-          tmaLoad4(buf + sg * 8u * planeBytes, &map, &fullBar[b], (int)(sg * (segBytes / 4u)), (int)(tl * (P.tileOut / 8)), 0,
+          tmaLoad4(buf + sg * 8u * planeBytes, &map, &fullBar[b], (int)(sg * (segBytes / 4u)), (int)(tl * (tileOut / 8)), 0,
                    (int)c);
         }
       }
     } else {
-      tmaStageSlow<NT, DT>(buf, P.x + (size_t)c * P.xStride, (unsigned long long)tl * P.tileOut * D, rowsStaged, planeBytes, P);
+      tmaStageSlow<NT, DT>(buf, P.x + (size_t)c * P.xStride, (unsigned long long)tl * tileOut * D, rowsStaged, planeBytes, P);
     }
   };
 
@@ -640,7 +643,7 @@ __global__ void __launch_bounds__(TG* PSPLIT, MINB)
   for (unsigned it = 0; chan < P.numChannels; it++) {
     const unsigned b = (NBUF == 2) ? (it & 1u) : 0u;
     unsigned char* buf = bufBase + b * bufBytes;
-    const unsigned long long o0 = (unsigned long long)tile * P.tileOut;
+    const unsigned long long o0 = (unsigned long long)tile * tileOut;
     unsigned nextChan = chan, nextTile = tile;
     advance(nextChan, nextTile);
     if (NBUF == 2) {
@@ -719,7 +722,7 @@ __global__ void __launch_bounds__(TG* PSPLIT, MINB)
       const unsigned long long ob = o0 + (unsigned long long)t * kTmaR;
       if (GSDR_DBG(P) & 4u) {
         if (acc[0].x == 123.456f) P.y[(size_t)chan * P.yStride] = acc[1];  // measurement hook: no output traffic
-      } else if (P.epi == kEpiFmDemod) {
+      } else if (kHasEpilogue && P.epi == kEpiFmDemod) {
         // d[n] = gain * arg(y[n+1] * conj(y[n])) (ref: src/quad_demod.cu:23-37, src/fm.cu:58-68): the successor of this
         // thread's last output is the next thread's first one; the tile's last thread only supplies it (its own
         // outputs belong to the next tile, which starts 8 outputs before this one ends)
@@ -730,8 +733,10 @@ __global__ void __launch_bounds__(TG* PSPLIT, MINB)
 #pragma unroll
         for (int r = 0; r < 8; r++) v[r] = quadFmValue(acc[r], r < 7 ? acc[r + 1] : nx, P.epiGain);
         if (t + 1 < (unsigned)TG) tmaStoreReal(P, chan, ob, v, P.nOut - 1);  // nOut low-pass values, nOut - 1 phase steps
-      } else {
+      } else if (kHasEpilogue) {
         tmaStoreTile(P, chan, ob, acc);
+      } else {
+        tmaStoreComplex(P, chan, ob, acc);
       }
     }
     chan = nextChan;
@@ -1575,6 +1580,141 @@ __global__ void __launch_bounds__(TG* PSPLIT + 32 * MIXW, MINB) firTmaInt8Kernel
         }
       }
     }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// One input, K frequency shifts (the idea of the reference's dead k_Fm4x, ref: src/fm.cu:71-179):
+//     out_k[n] = sum_i x[nD + i] * exp(j * phase_k(first + nD + i)) * h[i],   k < K <= 16
+// The window of a tile is fetched from HBM ONCE (tensor copy into a raw buffer) and mixed K times, each time into the
+// work buffer the FIR then reads, so the wideband input crosses HBM once instead of K times.  Per shift the arithmetic
+// is exactly gsdrAdjustFrequencyFirFC's (row anchor x per-shift rotation table, firComputePairs), hence the outputs are
+// bit-identical to K separate calls through firTmaKernel with the same tile shape.
+// What it buys is measured in profiles/r02/channelizer.jsonl: little where the FIR is issue-bound (32 taps per input
+// sample), up to the HBM ratio for short filters.
+// ---------------------------------------------------------------------------------------------------------
+constexpr unsigned kChanMaxShifts = 16;
+struct ChanParams : TmaParams {
+  unsigned numShifts;
+  unsigned long long yShiftStride;  // elements between the output arrays of consecutive shifts
+  unsigned long long steps[kChanMaxShifts];
+};
+
+template <int TG, int PSPLIT, int DT, int MINB>
+__global__ void __launch_bounds__(TG* PSPLIT, MINB)
+    firTmaChannelizerKernel(const __grid_constant__ CUtensorMap map, const ChanParams P) {
+  static_assert(DT != 0 && DT <= 16, "compile-time decimation, rows of one segment");
+  static_assert(MixStatic<TG * PSPLIT, DT>::ok, "needs the register-resident mixer");
+  constexpr unsigned NT = TG * PSPLIT;
+  constexpr unsigned BOUT = kTmaR * TG;
+  constexpr unsigned D = DT;
+  constexpr unsigned planeBytes = tmaPlaneRows(TG, kTmaJpadCap, DT) * tmaSegBytes(DT);
+  constexpr unsigned bufBytes = 8u * planeBytes;
+  extern __shared__ __align__(16) unsigned char smemRaw[];
+  __shared__ __align__(8) unsigned long long fullBar;
+  unsigned char* raw = smemRaw + ((1024u - (smemU32(smemRaw) & 1023u)) & 1023u);
+  unsigned char* work = raw + bufBytes;
+  float4* scratch = reinterpret_cast<float4*>(work + bufBytes);
+  float* hs = reinterpret_cast<float*>(scratch + (PSPLIT - 1) * (kTmaR / 2) * TG);
+  float2* ncoA = reinterpret_cast<float2*>(hs + (size_t)D * P.Jpad + 32u);
+  float2* ncoR = ncoA + (BOUT + P.Jpad);  // [numShifts][D]
+
+  const unsigned tid = threadIdx.x;
+  const unsigned grp = tid / TG;
+  const unsigned t = tid - grp * TG;
+  constexpr unsigned numPairs = D >> 1;
+  const unsigned ppBegin = (grp * numPairs) / PSPLIT;
+  const unsigned ppEnd = ((grp + 1) * numPairs) / PSPLIT;
+  const unsigned rowsStaged = BOUT + P.Jpad;
+  const unsigned mhCount = rowsStaged >> 3;
+
+  if (tid == 0) {
+    mbarInit(&fullBar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  for (unsigned i = tid; i < P.numShifts * D; i += NT) {
+    ncoR[i] = ncoExactPhasor((unsigned long long)(i % D), P.steps[i / D]);
+  }
+  {
+    const unsigned nh = D * P.Jpad;
+    for (unsigned i = tid; i < nh + 32u; i += NT) {
+      const unsigned pp = i / (2u * P.Jpad);
+      const unsigned rem = i - pp * 2u * P.Jpad;
+      const unsigned ti = (rem >> 1) * D + 2u * pp + (rem & 1u);
+      hs[i] = (i < nh && ti < P.T) ? __ldg(P.h + ti) : 0.0f;
+    }
+  }
+  __syncthreads();
+
+  unsigned phase = 0;
+  for (unsigned tile = blockIdx.x; tile < P.tilesPerChannel; tile += gridDim.x) {
+    const unsigned long long o0 = (unsigned long long)tile * BOUT;
+    const unsigned long long in0 = o0 * D;
+    if (tile * BOUT + rowsStaged <= P.tmaRows) {
+      if (tid == 0) {
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        mbarExpectTx(&fullBar, bufBytes);
+        tmaLoad4(raw, &map, &fullBar, 0, (int)(tile * (BOUT / 8)), 0, 0);
+      }
+      mbarWait(&fullBar, phase);
+      phase ^= 1u;
+    } else {
+      tmaStageSlow<NT, DT>(raw, P.x, in0, rowsStaged, planeBytes, P);
+      cpAsyncCommitWaitAll();
+      __syncthreads();
+    }
+    for (unsigned k = 0; k < P.numShifts; k++) {
+      const unsigned long long step = P.steps[k];
+      for (unsigned m = tid; m < rowsStaged; m += NT) {
+        ncoA[(m & 7u) * mhCount + (m >> 3)] = ncoExactPhasor(P.ncoFirst + in0 + (unsigned long long)m * D, step);
+      }
+      __syncthreads();  // anchors written; every thread has left the work buffer (FIR of the previous shift)
+      tmaMixRowsStatic<NT, DT>(raw, mhCount, planeBytes, ncoA, ncoR + k * D, P, tid, (int)bufBytes);
+      __syncthreads();
+      float2 acc[kTmaR];
+#pragma unroll
+      for (int r = 0; r < kTmaR; r++) acc[r] = make_float2(0.0f, 0.0f);
+      if (ppBegin < ppEnd) firComputePairs<DT>(acc, work, hs, t, ppBegin, ppEnd, P.Jpad, planeBytes, P);
+      if (PSPLIT > 1) {
+        if (grp > 0) {
+#pragma unroll
+          for (int q = 0; q < kTmaR / 2; q++) {
+            scratch[((grp - 1) * (kTmaR / 2) + q) * TG + t] =
+                make_float4(acc[2 * q].x, acc[2 * q].y, acc[2 * q + 1].x, acc[2 * q + 1].y);
+          }
+        }
+        __syncthreads();
+        if (grp == 0) {
+#pragma unroll
+          for (int g = 1; g < PSPLIT; g++) {
+#pragma unroll
+            for (int q = 0; q < kTmaR / 2; q++) {
+              const float4 w = scratch[((g - 1) * (kTmaR / 2) + q) * TG + t];
+              acc[2 * q].x += w.x;
+              acc[2 * q].y += w.y;
+              acc[2 * q + 1].x += w.z;
+              acc[2 * q + 1].y += w.w;
+            }
+          }
+        }
+      }
+      if (grp == 0) {
+        const unsigned long long ob = o0 + (unsigned long long)t * kTmaR;
+        float2* y = P.y + (size_t)k * P.yShiftStride;
+        if (P.y16 && ob + kTmaR <= P.nOut) {
+#pragma unroll
+          for (int r = 0; r < kTmaR; r += 2) {
+            *reinterpret_cast<float4*>(y + ob + r) = make_float4(acc[r].x, acc[r].y, acc[r + 1].x, acc[r + 1].y);
+          }
+        } else {
+#pragma unroll
+          for (int r = 0; r < kTmaR; r++) {
+            if (ob + r < P.nOut) y[ob + r] = acc[r];
+          }
+        }
+      }
+    }
+    __syncthreads();  // the last shift's mix has read the raw window: the next tile's copy may overwrite it
   }
 }
 

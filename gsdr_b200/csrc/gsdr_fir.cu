@@ -77,8 +77,11 @@ static constexpr PolyVariant kVariants[] = {
 };
 static constexpr int kNumVariants = (int)(sizeof(kVariants) / sizeof(kVariants[0]));
 
+constexpr int kForceFusedChannelizer = -5;  // tuning hook value: gsdrChannelizeFC through firTmaChannelizerKernel
 constexpr int kForceTensorCore = -4;  // tuning hook value: tensor-core kernel wherever its shape rules allow
 constexpr int kForceNoTensorCore = -3;  // tuning hook value: automatic choice among the FFMA2 kernels only
+// launchTma's answer when the driver rejects the tensor map: the caller goes on to the kernels that need none
+constexpr cudaError_t kTmaEncodeFailed = (cudaError_t)0x7f0000e1;
 // Tuning build only (-DGSDR_B200_TUNING): process-wide variant override and work-skipping measurement flags.  The
 // release library has neither the state nor the setters; forcedVariant() / debugFlags() fold to constants there.
 #ifdef GSDR_B200_TUNING
@@ -94,7 +97,7 @@ static inline unsigned debugFlags() noexcept { return 0u; }
 // the override as the FFMA2-kernel choosers see it: the two tensor-core values mean "automatic" to them
 static inline int forcedFfmaVariant() noexcept {
   const int f = forcedVariant();
-  return (f == kForceTensorCore || f == kForceNoTensorCore) ? -1 : f;
+  return (f == kForceTensorCore || f == kForceNoTensorCore || f == kForceFusedChannelizer) ? -1 : f;
 }
 
 struct DeviceInfo {
@@ -151,7 +154,8 @@ static cudaError_t launchPolyT(PolyParams& P, size_t smem, int dev, int smCount,
     configured[dev & 63].store(smem, std::memory_order_release);
   }
   int perSm = 0;
-  cudaError_t st = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, kernel, TG * PSPLIT, smem);
+  static OccCache occ;
+  cudaError_t st = occupancyCached(occ, kernel, TG * PSPLIT, smem, dev, &perSm);
   if (st != cudaSuccess) return report(st, "cudaOccupancyMaxActiveBlocksPerMultiprocessor");
   if (perSm < 1) return cudaErrorInvalidConfiguration;
   const unsigned long long resident = (unsigned long long)perSm * (unsigned)smCount;
@@ -460,11 +464,22 @@ static int chooseCcVariant(const FirCall& c, int maxSmem, TmaGeom* geom) noexcep
 }
 
 // variant: a TMA / fused-NCO variant id, or (ccVariant >= 0) a complex-tap variant
+// one input, several frequency shifts in one launch (firTmaChannelizerKernel)
+struct ChanExtra {
+  int tg, psplit;
+  unsigned numShifts;
+  unsigned long long yShiftStride;
+  const unsigned long long* steps;
+};
+
 static cudaError_t launchTma(const FirCall& c, int variant, const TmaGeom& geom, int dev, int smCount,
-                             cudaStream_t stream, int ccVariant = -1, int wideVariant = -1) noexcept {
+                             cudaStream_t stream, int ccVariant = -1, int wideVariant = -1,
+                             const ChanExtra* chan = nullptr) noexcept {
   TmaVariant v;
   int mixw = 0;
-  if (wideVariant >= 0) {
+  if (chan) {
+    v = TmaVariant{chan->tg, chan->psplit, 2, 1};
+  } else if (wideVariant >= 0) {
     if (wideVariant >= kNumWideVariants) return cudaErrorInvalidValue;
     v = TmaVariant{kWideVariants[wideVariant].tg, kWideVariants[wideVariant].psplit, 2, 1};
   } else if (ccVariant >= 0) {
@@ -536,12 +551,20 @@ static cudaError_t launchTma(const FirCall& c, int variant, const TmaGeom& geom,
     const CUresult r = encodeTiled()(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)c.input, gdim, gstride, box,
                                      estr, CU_TENSOR_MAP_INTERLEAVE_NONE, geom.swizzle,
                                      CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) {
-      std::fprintf(stderr, "gsdr-b200: cuTensorMapEncodeTiled failed with CUresult %d\n", (int)r);
-      return cudaErrorInvalidValue;
-    }
+    if (r != CUDA_SUCCESS) return kTmaEncodeFailed;  // e.g. a channel stride beyond the tensor map's 2^40 bytes
     if (tmaRows < 8) P.tmaRows = 0;
   }
+#ifdef GSDR_B200_TUNING
+  if (chan) {
+    ChanParams CP{};
+    static_cast<TmaParams&>(CP) = P;
+    CP.numShifts = chan->numShifts;
+    CP.yShiftStride = chan->yShiftStride;
+    if (chan->numShifts > 1 && (chan->yShiftStride * 8) % 16 != 0) CP.y16 = 0;  // odd stride: 8-byte stores
+    for (unsigned k = 0; k < chan->numShifts; k++) CP.steps[k] = chan->steps[k];
+    return launchChan((int)D, map, CP, geom.smemBytes, dev, smCount, stream);
+  }
+#endif
   if (wideVariant >= 0) {
     return launchWideDt32(c.nco == kNcoExact ? kPolyNcoExact : kPolyFC, wideVariant, map, P, geom.smemBytes, dev, smCount,
                           stream);
@@ -816,7 +839,7 @@ cudaError_t enqueueFir(const FirCall& c, cudaStream_t stream) noexcept {
   if (c.numOutputs == 0 || c.numChannels == 0) return cudaSuccess;
   if (c.decimation == 0) return cudaErrorInvalidValue;
   if (c.nco != kNcoNone && c.type != kFirFC) return cudaErrorInvalidValue;
-  if (c.epilogue != kFirEpiNone && (c.type != kFirFC || c.tapCount == 0)) return cudaErrorNotSupported;
+  if (c.epilogue != kFirEpiNone && (c.type != kFirFC || c.tapCount == 0 || c.nco != kNcoExact)) return cudaErrorNotSupported;
   if (c.tapCount == 0) {
     // the reference writes zero<OUT_T>() when the tap loop does not run (ref: src/fir.cu:67-70)
     for (size_t ch = 0; ch < c.numChannels; ch++) {
@@ -841,16 +864,26 @@ cudaError_t enqueueFir(const FirCall& c, cudaStream_t stream) noexcept {
 #endif
   {
     TmaGeom tg{};
+    // a tensor map the driver will not encode (kTmaEncodeFailed) sends the call on to the kernels that need none
     const int wv = chooseWideVariant(c, info->maxSmemOptin, &tg);
-    if (wv >= 0) return launchTma(c, -1, tg, dev, info->smCount, stream, -1, wv);
-    const int tv = chooseTmaVariant(c, info->maxSmemOptin, &tg);
-    if (tv >= 0) return launchTma(c, tv, tg, dev, info->smCount, stream);
+    if (wv >= 0) {
+      st = launchTma(c, -1, tg, dev, info->smCount, stream, -1, wv);
+      if (st != kTmaEncodeFailed) return st;
+    }
+    const int tv = wv >= 0 ? -1 : chooseTmaVariant(c, info->maxSmemOptin, &tg);
+    if (tv >= 0) {
+      st = launchTma(c, tv, tg, dev, info->smCount, stream);
+      if (st != kTmaEncodeFailed) return st;
+    }
     if (c.epilogue != kFirEpiNone) return cudaErrorNotSupported;  // only the TMA-fed kernels have fused output stages
     RealGeom rg{};
     const int rv = chooseRealVariant(c, info->maxSmemOptin, &rg);
     if (rv >= 0) return launchReal(c, rv, rg, dev, info->smCount, stream);
     const int cv = chooseCcVariant(c, info->maxSmemOptin, &tg);
-    if (cv >= 0) return launchTma(c, -1, tg, dev, info->smCount, stream, cv);
+    if (cv >= 0) {
+      st = launchTma(c, -1, tg, dev, info->smCount, stream, cv);
+      if (st != kTmaEncodeFailed) return st;
+    }
     const int fv = chooseCfVariant(c, info->maxSmemOptin, &rg);
     if (fv >= 0) return launchReal(c, -1, rg, dev, info->smCount, stream, fv);
   }
@@ -1003,6 +1036,70 @@ cudaError_t enqueueFirInt8(bool nco, float sampleRate, float frequencyShift, siz
   return cudaLaunchKernel(kernel, dim3((unsigned)bpc), dim3(kDirectThreads), args, 0, stream);
 }
 
+// One input, numShifts frequency shifts: the fused kernel where the shape allows (window fetched once per tile, mixed
+// and filtered per shift), otherwise one fused NCO + FIR call per shift.  Results are those of the separate calls.
+cudaError_t enqueueChannelizer(float sampleRate, const float* frequencyShifts, size_t numShifts, size_t firstSampleIndex,
+                               size_t decimation, const float* taps, size_t tapCount, const cuComplex* input,
+                               cuComplex* output, size_t outputStride, size_t numOutputs, cudaStream_t stream) noexcept {
+  if (numOutputs == 0 || numShifts == 0) return cudaSuccess;
+  if (decimation == 0 || !frequencyShifts) return cudaErrorInvalidValue;
+  FirCall c;
+  c.type = kFirFC;
+  c.nco = kNcoExact;
+  c.decimation = decimation;
+  c.taps = taps;
+  c.tapCount = tapCount;
+  c.input = input;
+  c.numOutputs = numOutputs;
+  c.sampleRate = sampleRate;
+  c.firstSampleIndex = firstSampleIndex;
+  int dev = 0;
+  cudaError_t st = cudaGetDevice(&dev);
+  if (st != cudaSuccess) return st;
+  const DeviceInfo* info = deviceInfo(dev);
+  if (!info || info->status != cudaSuccess) return info ? info->status : cudaErrorInvalidDevice;
+  const ChanShape* shape = nullptr;
+  for (const ChanShape& sh : kChanShapes)
+    if ((size_t)sh.D == decimation) shape = &sh;
+  TmaGeom geom{};
+  // Measured and NOT adopted (profiles/r02/channelizer.jsonl: 0.84-1.02 x the speed of the per-shift launches —
+  // the FIR is issue-bound for every tap count, so fetching the window once buys nothing): the fused kernel exists in
+  // the tuning build only, behind the override.
+#ifdef GSDR_B200_TUNING
+  bool fused = forcedVariant() == kForceFusedChannelizer && shape && tapCount > 0 && encodeTiled() &&
+               (uintptr_t)input % 16 == 0 && numOutputs < 0xfff00000ull &&
+               tmaGeometry(TmaVariant{shape->tg, shape->psplit, 2, 1}, decimation, tapCount, &geom) && geom.staticD;
+#else
+  bool fused = false;
+#endif
+  if (fused) {
+    // single partial-sum scratch instead of the double one; one rotation table per shift
+    const size_t maxShifts = numShifts < kChanMaxShifts ? numShifts : kChanMaxShifts;
+    geom.smemBytes += (maxShifts - 1) * decimation * 8;
+    fused = geom.smemBytes <= (size_t)info->maxSmemOptin;
+  }
+  for (size_t k0 = 0; k0 < numShifts; k0 += kChanMaxShifts) {
+    const size_t n = numShifts - k0 < kChanMaxShifts ? numShifts - k0 : kChanMaxShifts;
+    bool done = false;
+    if (fused) {
+      unsigned long long steps[kChanMaxShifts];
+      for (size_t k = 0; k < n; k++) steps[k] = ncoPhaseStep(frequencyShifts[k0 + k], sampleRate);
+      ChanExtra ex{shape->tg, shape->psplit, (unsigned)n, (unsigned long long)outputStride, steps};
+      c.output = output + k0 * outputStride;
+      st = launchTma(c, -1, geom, dev, info->smCount, stream, -1, -1, &ex);
+      if (st == cudaSuccess) done = true;
+      else if (st != kTmaEncodeFailed) return st;
+    }
+    for (size_t k = 0; !done && k < n; k++) {
+      c.frequencyShift = frequencyShifts[k0 + k];
+      c.output = output + (k0 + k) * outputStride;
+      st = enqueueFir(c, stream);
+      if (st != cudaSuccess) return st;
+    }
+  }
+  return cudaSuccess;
+}
+
 static cudaError_t firEntry(FirType type, size_t decimation, const void* taps, size_t tapCount, const void* input,
                             void* output, size_t numOutputs, int32_t cudaDevice, cudaStream_t stream) noexcept {
   DeviceScope scope(cudaDevice);
@@ -1091,6 +1188,17 @@ GSDR_C_LINKAGE uint64_t gsdrNcoPhaseStep(float frequencyShift, float sampleRate)
   return ncoPhaseStep(frequencyShift, sampleRate);
 }
 
+GSDR_C_LINKAGE cudaError_t gsdrChannelizeFC(float sampleRate, const float* frequencyShifts, size_t numShifts,
+                                            size_t firstSampleIndex, size_t decimation, const float* taps,
+                                            size_t tapCount, const cuComplex* input, cuComplex* output,
+                                            size_t outputStride, size_t numOutputs, int32_t cudaDevice,
+                                            cudaStream_t cudaStream) GSDR_NO_EXCEPT {
+  DeviceScope scope(cudaDevice);
+  if (scope.status() != cudaSuccess) return scope.status();
+  return enqueueChannelizer(sampleRate, frequencyShifts, numShifts, firstSampleIndex, decimation, taps, tapCount, input,
+                            output, outputStride, numOutputs, cudaStream);
+}
+
 // ---- <gsdr/conversion.h> ---------------------------------------------------------------------------------
 
 GSDR_C_LINKAGE cudaError_t gsdrInt8ToNormFloat(const int8_t* input, float* output, size_t numElements,
@@ -1130,7 +1238,7 @@ GSDR_C_LINKAGE cudaError_t gsdrAdjustFrequencyFirFCInt8(float sampleRate, float 
 
 #ifdef GSDR_B200_TUNING
 GSDR_C_LINKAGE int gsdrB200SetKernelVariant(int variant) GSDR_NO_EXCEPT {
-  if (variant < -4 || variant >= firstWideVariantId() + kNumWideVariants) return -1;
+  if (variant < -5 || variant >= firstWideVariantId() + kNumWideVariants) return -1;
   gForcedVariant.store(variant, std::memory_order_relaxed);
   return 0;
 }

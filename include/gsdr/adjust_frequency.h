@@ -76,4 +76,28 @@ GSDR_C_LINKAGE GSDR_PUBLIC cudaError_t gsdrAdjustFrequencyFirFCLiteral(
  */
 GSDR_C_LINKAGE GSDR_PUBLIC uint64_t gsdrNcoPhaseStep(float frequencyShift, float sampleRate) GSDR_NO_EXCEPT;
 
+/*
+ * One input, numShifts channels (the idea of the reference's dead k_Fm4x, ref: src/fm.cu:71-179):
+ *     output[k * outputStride + n] = gsdrAdjustFrequencyFirFC(sampleRate, frequencyShifts[k], ...)[n]
+ * frequencyShifts is a HOST array; everything else as in gsdrAdjustFrequencyFirFC.  One fused NCO + FIR launch per
+ * shift is enqueued on cudaStream (capturable), so the outputs ARE those of the separate calls.  A kernel that fetches
+ * each tile's window once and mixes + filters it per shift was built and measured (decimations 4, 8, 10, up to 16
+ * shifts per launch; bit-identical outputs): 0.84-1.02 x the speed of the per-shift launches, because the FIR is bound
+ * by FP32 issue slots, not by HBM, for every tap count — it is kept in the tuning build only.
+ */
+GSDR_C_LINKAGE GSDR_PUBLIC cudaError_t gsdrChannelizeFC(
+    float sampleRate,
+    const float* frequencyShifts,
+    size_t numShifts,
+    size_t firstSampleIndex,
+    size_t decimation,
+    const float* taps,
+    size_t tapCount,
+    const cuComplex* input,
+    cuComplex* output,
+    size_t outputStride,
+    size_t numOutputs,
+    int32_t cudaDevice,
+    cudaStream_t cudaStream) GSDR_NO_EXCEPT;
+
 #endif /* GSDR_B200_INCLUDE_GSDR_ADJUST_FREQUENCY_H_ */

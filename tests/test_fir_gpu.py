@@ -681,3 +681,26 @@ def test_sample_indices_beyond_2_to_31(kind, D, T, cuda_device):
         assert np.abs(got - want).max() <= _tol(taps, xs), f"outputs {o0}.."
     del dx, dy
     torch.cuda.empty_cache()
+
+
+@pytest.mark.parametrize("D,T", [(8, 255), (10, 255), (32, 1023), (4, 127), (5, 63)])
+@pytest.mark.parametrize("bad", [float("inf"), float("nan")])
+def test_non_finite_sample_reach_is_pinned(D, T, bad, cuda_device):
+    """Documented deviation (include/gsdr/fir.h): the staged kernels multiply zero-padded taps with real samples, so a
+    non-finite sample also poisons outputs whose window ends up to 16*D samples BEFORE it (0 * Inf = NaN); the
+    reference (ref: src/fir.cu:57-70) touches a sample only for the outputs whose T taps cover it.  Pinned here: every
+    output the reference would poison is non-finite, nothing after the sample's last window is touched, and the extra
+    reach before it is at most 16 outputs."""
+    n_out = 40_000
+    n_in = g.fir_num_inputs(n_out, T, D)
+    taps = synth.lowpass_taps(T, D)
+    x = synth.tone_plus_noise(0, n_in, seed=88)
+    k = 20_011 * D + 3
+    x[k] = complex(bad, 0.25)
+    y = _run("fc", D, taps, x, n_out, cuda_device)
+    finite = np.isfinite(y.real) & np.isfinite(y.imag)
+    first = max(0, -(-(k - T + 1) // D))   # smallest n with n*D + T > k
+    last = k // D                          # largest n with n*D <= k
+    assert not finite[first:last + 1].any(), "every output whose taps cover the sample is non-finite"
+    assert finite[last + 1:].all(), "no output that starts after the sample is touched"
+    assert finite[:max(0, first - 16)].all(), "the padded taps reach at most 16 outputs further back"
