@@ -273,6 +273,13 @@ def case_fc(c: Ctx, name: str, steps: int, warmup: int, keep=False) -> dict:
             g.gsdrFirFC(D, dtaps, T, x, y, sh.numOutputs, c.local, c.stream)
     mine, ms, clocks = c.time_steps(step, steps, warmup)
     y_timed = y.clone()  # what the timed launches wrote
+    sustained = None
+    if keep:
+        # the timed region of K steps lasts a few milliseconds: too short for more than a couple of clock samples.  A
+        # second, longer loop of the same launches (about 0.3 s) shows what the clocks do under sustained load.
+        k_long = max(steps, int(300.0 / max(ms, 1e-3)))
+        s_mine, s_ms, s_clocks = c.time_steps(step, k_long, 0)
+        sustained = {"steps": k_long, "ms_per_step": s_ms, "value": n_in_total / (s_ms * 1e-3) / 1e6, "clocks": s_clocks}
     parity = bl.check_fir_windows("fc", D, taps, x, y_timed, sh.numOutputs,
                                   nco=(bl.NCO_FS, bl.NCO_SHIFT, sh.firstSampleIndex) if wl["nco"] else None)
     traffic = None
@@ -289,6 +296,8 @@ def case_fc(c: Ctx, name: str, steps: int, warmup: int, keep=False) -> dict:
     out = {"ms_per_step": ms, "value": n_in_total / (ms * 1e-3) / 1e6, "unit": UNIT, "scaling": "weak",
            "roofline": roof, "parity": parity, "clocks": clocks, "gpu_launches": steps, "kernel": _kernel_text(g, info),
            "config": bl.config_block(name, c.world)}
+    if sustained is not None:
+        out["sustained"] = sustained
     if keep:
         out["_state"] = dict(x=x, y=y, y_timed=y_timed, dtaps=dtaps, taps=taps, sh=sh, step=step,
                              n_in_total=n_in_total, n_out_total=n_out_total)
@@ -318,6 +327,22 @@ def case_cfg1(c: Ctx, steps: int, warmup: int) -> dict:
     cold, _, clocks = c.time_steps(step, k, warmup, flush_between=True)
     warm, _, _ = c.time_steps(step, 4 * k, warmup)
     floor, _, _ = c.time_steps(step_floor, 4 * k, warmup)
+    # the same launches replayed from a CUDA graph: what the device needs per launch once the host is out of the way
+    graph = t.cuda.CUDAGraph()
+    with t.cuda.graph(graph, stream=c.stream):
+        for _ in range(100):
+            step()
+    with t.cuda.stream(c.stream):
+        graph.replay()
+    c.stream.synchronize()
+    e0, e1 = t.cuda.Event(enable_timing=True), t.cuda.Event(enable_timing=True)
+    with t.cuda.stream(c.stream):
+        e0.record(c.stream)
+        for _ in range(5):
+            graph.replay()
+        e1.record(c.stream)
+    c.stream.synchronize()
+    graphed = e0.elapsed_time(e1) / 500.0
     want = None
     from oracle import oracle
     want = oracle.fir("ff", D, taps, x.cpu().numpy(), n_out, f64=True)
@@ -329,6 +354,7 @@ def case_cfg1(c: Ctx, steps: int, warmup: int) -> dict:
     return {"ms_per_step": cold, "value": n_in / (cold * 1e-3) / 1e6, "unit": UNIT, "scaling": "single", "n_gpus": 1,
             "us_per_launch_cold_l2": cold * 1e3, "us_per_launch_back_to_back": warm * 1e3,
             "us_per_empty_launch_back_to_back": floor * 1e3, "launch_latency_share": floor / warm if warm > 0 else None,
+            "us_per_launch_cuda_graph": graphed * 1e3, "value_cuda_graph": n_in / (graphed * 1e-3) / 1e6,
             "roofline": roof, "parity": {"max_err": err, "tol": tol, "ok": bool(err <= tol), "windows": 1,
                                          "outputs_per_window": n_out, "against": "oracle f64, every output"},
             "clocks": clocks, "gpu_launches": k, "kernel": _kernel_text(g, info), "config": bl.config_block("cfg1", 1)}
@@ -444,7 +470,20 @@ def strong_scaling(c: Ctx, steps: int, warmup: int) -> dict:
     parity = bl.check_fir_windows("fc", D, taps, x0, y, sh.numOutputs)
     roof = bl.roofline(8 * sh.numInputs + 8 * sh.numOutputs + 4 * T, 4.0 * T * sh.numOutputs, mine * 1e-3, c.fp32_peak,
                        c.fp32_src)
-    return {"ms_per_step": ms, "value": n_in_total / (ms * 1e-3) / 1e6, "unit": UNIT, "scaling": "strong",
+    # the 67 MB of outputs of this capture collected on rank 0 (NCCL send/recv into the final buffer)
+    counts = [g.shard_plan_time(n_out_total, D, T, 0, c.world, r).numOutputs for r in range(c.world)]
+    firsts = [g.shard_plan_time(n_out_total, D, T, 0, c.world, r).firstOutput for r in range(c.world)]
+    full = t.zeros(n_out_total, dtype=t.complex64, device=c.dev) if c.rank == 0 else None
+    c.gd.gather_outputs_p2p(y, counts, firsts, full)
+    c.barrier()
+    g0, g1 = t.cuda.Event(enable_timing=True), t.cuda.Event(enable_timing=True)
+    g0.record()
+    for _ in range(5):
+        c.gd.gather_outputs_p2p(y, counts, firsts, full)
+    g1.record()
+    c.barrier()
+    gather_ms = c.max_ranks(g0.elapsed_time(g1) / 5)
+    return {"ms_per_step": ms, "gather_ms": gather_ms, "gather_bytes_to_rank0": 8 * (n_out_total - counts[0]), "value": n_in_total / (ms * 1e-3) / 1e6, "unit": UNIT, "scaling": "strong",
             "input_samples_total": n_in_total, "per_rank_us": [v * 1e3 for v in c.all_ranks(mine)],
             "launch": f"one CUDA graph of {steps} gsdrFirFC launches per rank",
             "l2": f"{copies} rotating input copies of {sh.numInputs * 8 >> 20} MiB per rank (> 2x the 126 MB L2 together)",
@@ -534,10 +573,27 @@ def e2e_block(c: Ctx, st: dict, steps: int, nco: bool) -> dict:
     t.cuda.synchronize(c.dev)
     dt = c.max_ranks(time.perf_counter() - t0)
     ok = bool(t.equal(yout.to(c.dev), st["y_timed"]))
+    # What the platform gives: the same input bytes as plain pinned-host -> device copies, all ranks at once, no kernel.
+    # e2e within a few percent of this = the host's PCIe / memory system is the limit, not the pipeline or the GPUs.
+    dst = t.empty_like(st["x"])
+    with t.cuda.stream(c.stream):
+        dst.copy_(xin, non_blocking=True)
+    c.barrier()
+    t0 = time.perf_counter()
+    with t.cuda.stream(c.stream):
+        for _ in range(n):
+            dst.copy_(xin, non_blocking=True)
+    c.stream.synchronize()
+    dt_copy = c.max_ranks(time.perf_counter() - t0)
+    del dst
+    copy_gbs = c.world * xin.numel() * 8 * n / dt_copy / 1e9
     res = {"value": st["n_in_total"] / (dt / n) / 1e6, "unit": UNIT, "h2d_bytes_per_step": xin.numel() * 8 + T * 4,
            "d2h_bytes_per_step": yout.numel() * 8, "ms_per_step": dt / n * 1e3, "steps": n,
            "timing": "host wall clock around the blocking API call (copies + kernels + sync), max over ranks",
-           "matches_device_path": ok, "numa_node_rank0": c.numa_node}
+           "matches_device_path": ok, "numa_node_rank0": c.numa_node,
+           "h2d_gb_s_all_ranks": c.world * (xin.numel() * 8) / (dt / n) / 1e9,
+           "plain_h2d_copy_gb_s_all_ranks": copy_gbs,
+           "fraction_of_plain_copy": (c.world * (xin.numel() * 8) / (dt / n) / 1e9) / copy_gbs}
     # the same capture as int8 I/Q (2 bytes per sample over PCIe instead of 8) through gsdrFirFCInt8Host
     if not nco and hasattr(pipe, "gsdrFirFCInt8Host"):
         xi8 = t.view_as_real(st["x"]).mul(127.0).round().clamp(-127, 127).to(t.int8).reshape(-1)

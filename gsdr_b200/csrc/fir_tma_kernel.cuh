@@ -59,6 +59,8 @@ struct TmaParams {
   unsigned long long ncoStep, ncoFirst;
   unsigned ncoFirst32;
   float ncoFs, ncoF;
+  unsigned long long ncoRow0;  // ncoFirst / D: absolute row number of the channel's first row (exact NCO)
+  unsigned ncoRho;             // ncoFirst % D: offset of every row's first sample inside its absolute row
 };
 
 // firTmaRealKernel: x, y and the strides count floats, D is twice the caller's decimation
@@ -304,6 +306,47 @@ __device__ __forceinline__ float2 cmulf(float2 a, float2 b) {
   return make_float2(__fmaf_rn(a.x, b.x, -__fmul_rn(a.y, b.y)), __fmaf_rn(a.x, b.y, __fmul_rn(a.y, b.x)));
 }
 
+// Barrier among the NT threads that build / mix a window: the whole CTA (id 0) or the producer warps only.
+template <int NT, int BARRIER_ID>
+__device__ __forceinline__ void mixBarrier() {
+  if (BARRIER_ID == 0) {
+    __syncthreads();
+  } else {
+    asm volatile("bar.sync %0, %1;" ::"n"(BARRIER_ID), "n"(NT) : "memory");
+  }
+}
+
+// Row anchors A[m] = exp(j * phase(first sample of row m)) of a window, two-level: one sincospi per EIGHT rows,
+//     A = coarse[a >> 3] * fine[a & 7],   a = absolute row number (row0 + m),
+// coarse[g] the phasor of the first sample of absolute row 8g, fine[i] = exp(j * i * D * step) a per-CTA table (fine[0]
+// is exactly 1).  A sincospi costs ~45 instructions, i.e. 5.6 per sample at D = 8 when taken per row; this way it is
+// ~1.  Grouping by ABSOLUTE row number keeps the anchor a pure function of the absolute sample index, so time shards and
+// stream blocks (which start at multiples of D from the capture's first sample) still reproduce the one-shot bits.
+// Layout of the anchors: [m & 7][m >> 3], read by pass 2 with consecutive lanes on consecutive row groups.
+// scratch: (rows / 8 + 2) float2.  Contains one barrier; the caller adds the one after it.
+template <int NT, int BARRIER_ID>
+__device__ __forceinline__ void ncoRowAnchors(float2* ncoA, float2* coarse, const float2* fine, unsigned rows,
+                                              unsigned mhCount, unsigned long long row0, unsigned D, unsigned rho,
+                                              unsigned long long step, unsigned lt) {
+  const unsigned long long g0 = row0 >> 3;
+  const unsigned groups = (unsigned)(((row0 + rows - 1u) >> 3) - g0) + 1u;
+  for (unsigned i = lt; i < groups; i += NT) coarse[i] = ncoExactPhasor(((g0 + i) << 3) * D + rho, step);
+  mixBarrier<NT, BARRIER_ID>();
+  const unsigned r7 = (unsigned)(row0 & 7ull);
+  for (unsigned m = lt; m < rows; m += NT) {
+    const unsigned a = r7 + m;
+    ncoA[(m & 7u) * mhCount + (m >> 3)] = cmulf(coarse[a >> 3], fine[a & 7u]);
+  }
+}
+
+// shared-memory carve-up of the exact NCO's tables behind the row anchors: R[p], p < D (padded to an even count), the
+// eight fine anchors, then the coarse-anchor scratch
+__device__ __forceinline__ float2* ncoFineOf(float2* ncoR, unsigned D) { return ncoR + D + (D & 1u); }
+__device__ __forceinline__ float2* ncoCoarseOf(float2* ncoR, unsigned D) { return ncoR + D + (D & 1u) + 8u; }
+__host__ __device__ constexpr unsigned ncoTableFloat2s(unsigned D, unsigned rows) {
+  return D + (D & 1u) + 8u + rows / 8u + 2u + ((rows / 8u) & 1u);  // even count: what follows stays 16-byte aligned
+}
+
 // In-place NCO mix of a landed window (all threads).  Element (m, p) is input sample in0 + m*D + p.
 //
 // Exact mode: phasor(row m, phase p) = A[m] * R[p] with A[m] = exp(j*phase(first sample of row m)) evaluated by
@@ -314,15 +357,6 @@ __device__ __forceinline__ float2 cmulf(float2 a, float2 b) {
 // plane, row group) with consecutive lanes on consecutive row groups, like the FIR reader (conflict free).
 // Literal mode (parity with the reference only): the reference's arithmetic per sample.
 // Barrier among the NT threads that run a mix pass: the whole CTA (id 0) or the mixer warps only (named barrier).
-template <int NT, int BARRIER_ID>
-__device__ __forceinline__ void mixBarrier() {
-  if (BARRIER_ID == 0) {
-    __syncthreads();
-  } else {
-    asm volatile("bar.sync %0, %1;" ::"n"(BARRIER_ID), "n"(NT) : "memory");
-  }
-}
-
 // Pass 2 of the exact mix for compile-time decimations.  A thread keeps ONE residue s = mh & 7 of the row groups and
 // one chunk of CH branch pairs for the whole window, so that
 //   * its rotation-table entries R[p] live in registers for the whole window (no table loads);
@@ -392,17 +426,16 @@ __device__ __forceinline__ void tmaMixRowsStatic(unsigned char* buf, unsigned mh
 }
 
 template <int MODE, int NT, int DT, int BARRIER_ID = 0>
-__device__ __forceinline__ void tmaMixWindow(unsigned char* buf, unsigned long long in0, unsigned rows,
-                                             unsigned planeBytes, float2* ncoA, const float2* ncoR,
-                                             const TmaParams& P, unsigned lt = threadIdx.x) {
+__device__ __forceinline__ void tmaMixWindow(unsigned char* buf, unsigned long long in0, unsigned long long row0,
+                                             unsigned rows, unsigned planeBytes, float2* ncoA, float2* ncoR,
+                                             const TmaParams& P, unsigned lt = threadIdx.x) {  // row0: in0 / D
   const unsigned D = DT ? (unsigned)DT : P.D;
   const unsigned pairsPerRow = D >> 1;
   if (MODE == kPolyNcoExact) {
     const unsigned mhCount = rows >> 3;  // rows is a multiple of 8
     // pass 1: row anchors, stored [ml][mh] so that pass 2 reads them with consecutive lanes
-    for (unsigned m = lt; m < rows; m += NT) {
-      ncoA[(m & 7u) * mhCount + (m >> 3)] = ncoExactPhasor(P.ncoFirst + in0 + (unsigned long long)m * D, P.ncoStep);
-    }
+    ncoRowAnchors<NT, BARRIER_ID>(ncoA, ncoCoarseOf(ncoR, D), ncoFineOf(ncoR, D), rows, mhCount, P.ncoRow0 + row0, D,
+                                  P.ncoRho, P.ncoStep, lt);
     mixBarrier<NT, BARRIER_ID>();
     if constexpr (MixStatic<NT, DT>::ok) {
       tmaMixRowsStatic<NT, DT>(buf, mhCount, planeBytes, ncoA, ncoR, P, lt);
@@ -590,6 +623,7 @@ __global__ void __launch_bounds__(TG* PSPLIT, MINB)
   }
   if (MODE == kPolyNcoExact) {
     for (unsigned p = tid; p < D; p += NT) ncoR[p] = ncoExactPhasor((unsigned long long)p, P.ncoStep);
+    for (unsigned p = tid; p < 8u; p += NT) ncoFineOf(ncoR, D)[p] = ncoExactPhasor((unsigned long long)p * D, P.ncoStep);
   }
   __syncthreads();
 #ifndef GSDR_NO_PDL
@@ -683,7 +717,7 @@ __global__ void __launch_bounds__(TG* PSPLIT, MINB)
       __syncthreads();
     }
     if (MODE == kPolyNcoExact || MODE == kPolyNcoLiteral) {
-      tmaMixWindow<MODE, NT, DT>(buf, o0 * D, rowsStaged, planeBytes, ncoA, ncoR, P);
+      tmaMixWindow<MODE, NT, DT>(buf, o0 * D, o0, rowsStaged, planeBytes, ncoA, ncoR, P);
       __syncthreads();
     }
 
@@ -787,6 +821,7 @@ __global__ void __launch_bounds__(TG* PSPLIT + 32 * MIXW, MINB)
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   for (unsigned p = tid; p < D; p += NTF + NTM) ncoR[p] = ncoExactPhasor((unsigned long long)p, P.ncoStep);
+  for (unsigned p = tid; p < 8u; p += NTF + NTM) ncoFineOf(ncoR, D)[p] = ncoExactPhasor((unsigned long long)p * D, P.ncoStep);
   {
     const unsigned nh = D * P.Jpad;
     for (unsigned i = tid; i < nh + 32u; i += NTF + NTM) {
@@ -836,8 +871,8 @@ __global__ void __launch_bounds__(TG* PSPLIT + 32 * MIXW, MINB)
         asm volatile("cp.async.wait_group 0;\n" ::: "memory");
         mixBarrier<NTM, 1>();
       }
-      tmaMixWindow<kPolyNcoExact, NTM, DT, 1>(buf, (unsigned long long)tile * BOUT * D, rowsStaged, planeBytes, ncoA,
-                                              ncoR, P, lt);
+      tmaMixWindow<kPolyNcoExact, NTM, DT, 1>(buf, (unsigned long long)tile * BOUT * D, (unsigned long long)tile * BOUT,
+                                              rowsStaged, planeBytes, ncoA, ncoR, P, lt);
       mbarArrive(&fullMix[b]);   // release: the mixed window is visible to whoever acquires the barrier
       mixBarrier<NTM, 1>();      // ncoA may be overwritten by the next tile's anchors
     }
@@ -1832,6 +1867,7 @@ __global__ void __launch_bounds__(TG* PSPLIT + 32 * MIXW, MINB)
   }
   if (kNco) {
     for (unsigned p = tid; p < D; p += NTF + NTM) ncoR[p] = ncoExactPhasor((unsigned long long)p, P.ncoStep);
+    for (unsigned p = tid; p < 8u; p += NTF + NTM) ncoFineOf(ncoR, D)[p] = ncoExactPhasor((unsigned long long)p * D, P.ncoStep);
   }
   {
     const unsigned nh = D * P.Jpad;
@@ -1910,9 +1946,8 @@ __global__ void __launch_bounds__(TG* PSPLIT + 32 * MIXW, MINB)
         unsigned char* buf = bufBase + b * stageBytes;
         mbarWait(&fullRaw[b], use & 1u);
         if (sg == 0) {  // row anchors of the tile, stored [ml][mh]
-          for (unsigned m = lt; m < rowsStaged; m += NTM) {
-            ncoA[(m & 7u) * mhCount + (m >> 3)] = ncoExactPhasor(P.ncoFirst + in0 + (unsigned long long)m * D, P.ncoStep);
-          }
+          ncoRowAnchors<NTM, 1>(ncoA, ncoCoarseOf(ncoR, D), ncoFineOf(ncoR, D), rowsStaged, mhCount,
+                                P.ncoRow0 + (unsigned long long)tile * BOUT, D, P.ncoRho, P.ncoStep, lt);
           mixBarrier<NTM, 1>();
         }
         tmaMixSegmentStatic<NTM, DT>(buf, sg, mhCount, planeBytes, ncoA, ncoR, P, lt);

@@ -263,7 +263,8 @@ static bool tmaGeometry(const TmaVariant& v, size_t D, size_t T, TmaGeom* g) noe
   g->planeBytes = (unsigned)(mhp * G);
   g->smemBytes = 1024 + (size_t)v.nbuf * (8 * D / G) * 8 * (size_t)g->planeBytes +
                  2 * (size_t)(v.psplit - 1) * v.tg * 64 + (D * Jpad + 32) * 4 +
-                 ((size_t)kTmaR * v.tg + Jpad + D) * 8;  // NCO row anchors + rotation table
+                 // NCO: row anchors, then rotation table + fine / coarse anchor tables
+                 ((size_t)kTmaR * v.tg + Jpad + ncoTableFloat2s((unsigned)D, (unsigned)(kTmaR * v.tg + Jpad))) * 8;
   return true;
 }
 
@@ -389,7 +390,7 @@ static bool wideGeometry(const SpecVariant& v, size_t D, size_t T, bool nco, Tma
   if (!tmaGeometry(shape, D, T, g) || !g->staticD) return false;
   // stage buffers (three with the NCO, two without; the partial-sum exchange reuses one), taps, row anchors + table
   g->smemBytes = 1024 + (nco ? 3 : 2) * 8 * (size_t)g->planeBytes + (D * g->Jpad + 32) * 4 +
-                 ((size_t)kTmaR * v.tg + g->Jpad + D) * 8;
+                 ((size_t)kTmaR * v.tg + g->Jpad + ncoTableFloat2s((unsigned)D, (unsigned)(kTmaR * v.tg + g->Jpad))) * 8;
   return true;
 }
 
@@ -537,6 +538,8 @@ static cudaError_t launchTma(const FirCall& c, int variant, const TmaGeom& geom,
   P.ncoFirst32 = (uint32_t)fmodf((float)c.firstSampleIndex, c.sampleRate);  // ref: src/fm.cu:202
   P.ncoFs = c.sampleRate;
   P.ncoF = c.frequencyShift;
+  P.ncoRow0 = (unsigned long long)c.firstSampleIndex / D;
+  P.ncoRho = (unsigned)((unsigned long long)c.firstSampleIndex % D);
 
   alignas(64) CUtensorMap map;
   {
