@@ -729,16 +729,20 @@ __global__ void __launch_bounds__(TG* PSPLIT, MINB)
 
     // Partial sums of the branch-pair groups go through a small double-buffered scratch area, so ONE barrier per
     // tile both publishes them and tells thread 0 that this window may be overwritten by the tile after next.
-    if (PSPLIT > 1 && grp > 0) {
+    // With two groups the collecting group alternates from tile to tile: the collector's extra work (partial-sum
+    // reads, stores) then loads the two warps' schedulers evenly (a + b == b + a: same bits either way).
+    const unsigned collector = (PSPLIT == 2) ? (it & 1u) : 0u;
+    if (PSPLIT > 1 && grp != collector) {
       float4* red = scratch + (size_t)(it & 1u) * (PSPLIT - 1) * (kTmaR / 2) * TG;
+      const unsigned slot = (PSPLIT == 2) ? 0u : grp - 1u;
 #pragma unroll
       for (int k = 0; k < kTmaR / 2; k++) {
-        red[((grp - 1) * (kTmaR / 2) + k) * TG + t] =
+        red[(slot * (kTmaR / 2) + k) * TG + t] =
             make_float4(acc[2 * k].x, acc[2 * k].y, acc[2 * k + 1].x, acc[2 * k + 1].y);
       }
     }
     __syncthreads();
-    if (grp == 0) {
+    if (grp == collector) {
       if (PSPLIT > 1) {
         const float4* red = scratch + (size_t)(it & 1u) * (PSPLIT - 1) * (kTmaR / 2) * TG;
 #pragma unroll
