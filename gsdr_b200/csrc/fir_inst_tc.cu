@@ -1,6 +1,7 @@
 // fir_inst_tc.cu — kernel instantiations and launcher of the tensor-core FIR (fir_tc_kernel.cuh).
-// Compiled into the tuning build only: the kernel was measured and not adopted.
+// Compiled into the tuning build only (DESIGN.md §4.3b holds the measurements and the decision).
 #ifdef GSDR_B200_TUNING
+// #define GSDR_TC_PHASE_TIMING 1   // per-phase cycle counts of two CTAs, printed by the kernel (diagnosis only)
 #include <atomic>
 #include <cstdio>
 #include <cstdlib>
@@ -48,13 +49,13 @@ static cudaError_t launchTcT(TcParams& P, size_t smem, int dev, int smCount, cud
 
 size_t tcSharedBytes(unsigned D, unsigned tablePitch) noexcept {
   const size_t raw = D == 4 ? TcGeom<4>::rawBytes : D == 8 ? TcGeom<8>::rawBytes : TcGeom<16>::rawBytes;
-  return raw + tcTableBytes(D, tablePitch);
+  return raw + tcTableBytes(tablePitch);
 }
 
 cudaError_t launchTc(unsigned D, TcParams& P, int dev, int smCount, cudaStream_t stream) noexcept {
   const size_t smem = tcSharedBytes(D, P.tablePitch);
   switch (D) {
-    case 4: return launchTcT<4, 4>(P, smem, dev, smCount, stream);
+    case 4: return launchTcT<4, 3>(P, smem, dev, smCount, stream);
     case 8: return launchTcT<8, 3>(P, smem, dev, smCount, stream);
     case 16: return launchTcT<16, 1>(P, smem, dev, smCount, stream);
     default: return cudaErrorInvalidValue;

@@ -1,46 +1,60 @@
 // fir_tc_kernel.cuh — decimating FIR, complex input x real taps (gsdrFirFC), on the 5th-generation tensor cores.
 // Replaces ref: src/fir.cu:49-71 (k_FirDecimate<cuComplex,cuComplex,float>) for shapes with many taps per output
-// (tapCount / decimation around 32: BASELINE configs 2 and 4), where the FFMA2 kernel of fir_tma_kernel.cuh is bound
-// by FP32 issue slots and this one by HBM.
+// (BASELINE configs 2 and 4), where the FFMA2 kernel of fir_tma_kernel.cuh is bound by FP32 issue slots.
 //
-// Formulation (banded Toeplitz GEMM, error-compensated TF32).  A window of S = 32 consecutive outputs starting at
-// output o0 reads the K = (S-1)*D + T consecutive samples starting at sample o0*D:
+// Formulation (banded Toeplitz GEMM).  A window of S = 32 consecutive outputs starting at output o0 reads the
+// K = (S-1)*D + T consecutive samples starting at sample o0*D:
 //     y[o0 + s] = sum_k x[o0*D + k] * h[k - s*D]                 (h = 0 outside [0, T))
-// i.e. D[row][s] = sum_k A[row][k] * B[k][s] with one ROW per (window, component): re and im are two real problems
-// sharing B.  FP32 accuracy comes from splitting both operands, x = xh + xl and h = hh + hl (xh, hh = the 11
-// significant bits tcgen05 keeps of an FP32 operand — it truncates —, xl, hl the exact remainders), and summing
-// all four partial products in the FP32 accumulator:
-//   * the M = 128 rows of one MMA are 32 windows x 2 components x {hi part, lo part} of the samples,
-//   * two MMAs per k-step, one against the hi taps and one against the lo taps, accumulate into the same tile,
-//   * the epilogue adds the hi-part row and the lo-part row of each (window, component).
-// tools/tc_probe.cu measures the pieces: truncation, descriptors, and an error of ~1e-6 relative for the split.
+// i.e. D[row][s] = sum_k A[row][k] * B[k][s] with one ROW per (window, component, part): re and im are two real
+// problems sharing B, and "part" is the FP16 head or remainder of the samples (below).
+//
+// Precision: FP16 operands, error-compensated.  tools/tc_probe.cu / tc_probe_f16.cu measured what the hardware gives:
+// a kind::tf32 MMA (K = 8) costs 26 + 0.46 N cycles whatever the accumulator pattern — 40.5 at N = 32 — while
+// kind::f16 (K = 16) runs at N/2 + 2 (17.3 at N = 32): per multiply-accumulate FP16 is ~5 x cheaper, which pays for
+// splitting.  Samples and taps are scaled by powers of two into [0.5, 1) (per tile / per call) and split,
+//     x*sx = xh + xl,   h*sh = hh + hl,   xh = top 11 significant bits (exact in FP16), xl = FP16(x*sx - xh),
+// and ALL FOUR partial products reach the FP32 accumulators (rows of both sample parts, two MMAs per k-step for the
+// two tap parts; the epilogue adds the head row and the remainder row), so nothing is dropped; what remains is the
+// FP16 rounding of the remainders: <= 2^-21 relative to a value near the tile's maximum, 2^-25 of that maximum for
+// small values — FP32-grade against BASELINE's tolerance 1e-5 * sum|h| * max|x| (tests/test_tc_gpu.py holds it to the
+// FFMA2 kernel's own error).  The epilogue undoes the two scales exactly.
+//
+// History of the design, all measured on BASELINE config 2 (FFMA2 kernel: 0.166 ms):
+//   v0  TF32 operands, hi/lo split, rows formed from FP32 samples per k-step: 0.2245 ms, bound by the MMAs
+//       (profiles/r02_tc_d8_fir_tensor_core_full.txt).
+//   v1  FP16 operands, S = 16, every row scaling / splitting / packing its own samples per k-step: 0.277 ms, bound by
+//       the 129 instructions per row-step of the producers (each sample is converted by the ~3 windows that overlap
+//       it; profiles/r02/tc_f16_v1_*).
+//   v2  (this file) every sample is converted ONCE per tile, in place, into four FP16 planes; forming a row is then
+//       four 16-byte shared-memory loads and one tcgen05.st.
 //
 // Operands.
-//   A comes from TENSOR MEMORY: four producer warps read the raw complex samples of the tile from shared memory
-//     (each byte is fetched from HBM exactly once per tile by 33 bulk copies; the two windows that overlap a sample
-//     both read it from shared memory), pick their component, form the hi / lo part and write 16 columns (two
-//     k-steps of 8) per stage with tcgen05.st; a 4-stage ring of TMEM columns decouples them from the MMA.
-//     Row (= TMEM lane) 32*w + l holds window 8*w + (l & 7), component (l >> 3) & 1, part l >> 4.
-//   B never exists as a matrix: B[k][s] depends on k - s*D only, so for every residue of k modulo D (in groups of
-//     four consecutive k = one 16-byte core-matrix row) ONE table T[u] = (h[(aMax-u)*D + off .. +3]) is kept in
-//     shared memory, and the K-major, un-swizzled descriptor of a k-step simply starts 16*(aMax - a) bytes into the
-//     table: rows s = 0..31 of the operand are the next 32 entries (16-byte row pitch, SBO = 128), the second
-//     k-group of the step is the next table (LBO = table pitch).  A few KB of taps serve every step of every tile.
+//   The copy warp brings the tile's raw complex samples into shared memory (each byte is fetched from HBM once per
+//     tile, by one bulk copy per segment of S*D samples).  The four producer warps find the tile's largest component,
+//     then rewrite every segment IN PLACE as four planes of S*D FP16 values: [re head | re remainder | im head | im
+//     remainder] (8 bytes per sample either way).
+//   A comes from TENSOR MEMORY: row (= TMEM lane) 32*w + l holds window 8*w + (l & 7), component (l >> 3) & 1, part
+//     l >> 4; per stage of 32 samples it loads 64 contiguous bytes of its plane and writes 16 columns with one
+//     tcgen05.st; a ring of TMEM stages decouples the producers from the MMAs.
+//   B never exists as a matrix: B[k][s] depends on k - s*D only, so per tap part TWO tables are kept in shared
+//     memory, T_tb[u] = (h[(aMax-u)*D + 8*tb + e])_{e<8} for the first and second group of eight k of a k-step; the
+//     K-major, un-swizzled descriptor of a k-step starts 16*(aMax - a) bytes into table 0 (rows s = 0..31 of the
+//     operand are the next 32 entries: 16-byte row pitch, SBO = 128; LBO = table pitch).  A few KB serve every step.
 //   D (128 x 32 FP32) lives in TMEM; the producer warps read it back with tcgen05.ld when the tile's last MMA has
 //     been committed.
-// Useful MACs / issued MACs = T / K (about one half) x 3/4 (the lo*lo product is computed but not needed), and the
-// kernel still has 1.5x headroom over the HBM time of config 2, which is what bounds it.
+// A tile is 1024 outputs (32 windows) of one channel; CTAs are persistent over tiles, up to 3-4 per SM (shared memory:
+// 33 segments + 16 bytes of padding each, so the 8 windows a warp reads hit different banks) — while one CTA
+// computes, another's bulk copies are in flight.  Segments that reach past the caller-guaranteed input are staged by
+// the copy warp with guarded loads and zero fill, and the epilogue masks outputs >= numOutputs: every output of a
+// call goes through the same arithmetic whatever its position in a tile.  (Results still depend on the TILE through
+// its scale factor and the k-step alignment, so time shards reproduce the unsharded call within the tolerance, not
+// bit for bit.)
 //
-// A tile is 1024 outputs (32 windows) of one channel; CTAs are persistent over tiles, 2-4 CTAs per SM (shared
-// memory: 33 sample segments of S*D samples + 16 bytes of padding each, so the 8 windows a warp reads hit
-// different banks) — while one CTA computes, the other's bulk copies are in flight.  Segments that reach past the
-// caller-guaranteed input (the last tile or two of a channel) are staged by the copy warp with guarded loads and zero
-// fill instead of a bulk copy, and the epilogue masks outputs >= numOutputs: every output of a call goes through the
-// same arithmetic, whatever its position — which is what makes time shards reproduce the unsharded bits.
-//
-// Non-finite samples: a window's Inf/NaN reaches all 32 outputs of its window row (0 * Inf in the band's zeros);
-// the reference would confine it to the outputs whose taps overlap it (documented in include/gsdr/fir.h).
+// Non-finite samples: a tile that contains an Inf/NaN keeps scale 1; the value reaches all outputs of its window rows
+// (0 * Inf in the band's zeros); the reference would confine it to the outputs whose taps overlap it.
 #pragma once
+
+#include <cuda_fp16.h>
 
 #include "fir_tma_kernel.cuh"
 
@@ -54,33 +68,33 @@ struct TcParams {
   unsigned long long xStride, yStride;  // channel strides, elements
   unsigned tilesPerChannel, totalTiles;
   unsigned T;
-  unsigned numStages;   // 16-sample stages per tile: ceil(((S-1)*D + T) / 16)
-  unsigned aMax;        // largest (8*j) / D over the tile's k-steps j
-  unsigned tablePitch;  // bytes between the tables of consecutive k-groups: (aMax + S) * 16
+  unsigned numStages;   // stages of 32 samples (two k-steps of 16) per tile: ceil(((S-1)*D + T) / 32)
+  unsigned aMax;        // (16 * (2 * numStages - 1)) / D: tap-row offset of the last k-step
+  unsigned tablePitch;  // bytes between the two tables of a tap part: (aMax + S) * 16
 };
 
 constexpr int kTcS = 32;          // outputs per window = MMA N
 constexpr int kTcWindows = 32;    // windows per tile
 constexpr int kTcTileOut = kTcS * kTcWindows;
-constexpr int kTcRing = 4;        // TMEM stages of 16 columns
-constexpr int kTcThreads = 192;   // warps 0-3: producers + epilogue, warp 4: MMA issue, warp 5: bulk copies
+constexpr int kTcRing = 4;        // TMEM stages of 16 columns (next to two accumulators of 32)
+constexpr int kTcProducers = 256;  // warps 0-7: two warpgroups of producers + epilogue (warp w and w + 4 share the
+                                   // TMEM lanes 32 * (w & 3) ..: the groups take alternate stages)
+constexpr int kTcThreads = kTcProducers + 64;  // warp 8: MMA issue, warp 9: bulk copies
 constexpr unsigned kTcTmemCols = 128;
 
 template <int D>
 struct TcGeom {
-  static_assert(D == 4 || D == 8 || D == 16, "segment must fit shared memory; k-groups must not straddle rows");
+  static_assert(D == 4 || D == 8 || D == 16, "k-steps of 16 samples must start on a tap row");
   static constexpr unsigned SD = kTcS * D;             // samples per segment = window stride
-  static constexpr unsigned segBytes = SD * 8;
+  static constexpr unsigned segBytes = SD * 8;         // raw: SD complex FP32; converted: four planes of SD FP16
+  static constexpr unsigned planeBytes = SD * 2;
   static constexpr unsigned segPitch = segBytes + 16;  // 16 bytes of padding: consecutive windows, different banks
   static constexpr unsigned numSegs = kTcWindows + 1;
   static constexpr unsigned rawBytes = numSegs * segPitch;
-  static constexpr unsigned numTables = (D >= 8 ? D : 8) / 4;
-  static constexpr unsigned maxTaps = SD + D;          // the window must fit two segments
+  static constexpr unsigned maxTaps = SD + D;          // (S-1)*D + T <= 2 * SD: a window fits two segments
 };
 
-__host__ __device__ inline unsigned tcTableBytes(unsigned D, unsigned tablePitch) {
-  return 2u * ((D >= 8 ? D : 8) / 4) * tablePitch;  // hi and lo parts
-}
+__host__ __device__ inline unsigned tcTableBytes(unsigned tablePitch) { return 4u * tablePitch; }  // {head, rem} x 2
 
 __device__ __forceinline__ unsigned tcElectOne() {
   unsigned pred;
@@ -93,13 +107,13 @@ __device__ __forceinline__ unsigned tcElectOne() {
       : "=r"(pred));
   return pred;
 }
-__device__ __forceinline__ void tcMma(unsigned dTmem, unsigned aTmem, unsigned long long bDesc, unsigned idesc,
-                                      unsigned accumulate) {
+__device__ __forceinline__ void tcMmaF16(unsigned dTmem, unsigned aTmem, unsigned long long bDesc, unsigned idesc,
+                                         unsigned accumulate) {
   asm volatile(
       "{\n"
       ".reg .pred p;\n"
       "setp.ne.b32 p, %4, 0;\n"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n"
       "}\n" ::"r"(dTmem),
       "r"(aTmem), "l"(bDesc), "r"(idesc), "r"(accumulate)
       : "memory");
@@ -111,69 +125,115 @@ __device__ __forceinline__ void tcCommit(unsigned long long* bar) {
 __device__ __forceinline__ void tcFenceBefore() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tcFenceAfter() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
-__device__ __forceinline__ void tcStore16(unsigned taddr, const unsigned (&v)[16]) {
+__device__ __forceinline__ void tcStore16(unsigned taddr, const uint4 (&v)[4]) {
   asm volatile(
       "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
       "%16};" ::"r"(taddr),
-      "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]),
-      "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+      "r"(v[0].x), "r"(v[0].y), "r"(v[0].z), "r"(v[0].w), "r"(v[1].x), "r"(v[1].y), "r"(v[1].z), "r"(v[1].w),
+      "r"(v[2].x), "r"(v[2].y), "r"(v[2].z), "r"(v[2].w), "r"(v[3].x), "r"(v[3].y), "r"(v[3].z), "r"(v[3].w)
       : "memory");
 }
-__device__ __forceinline__ void tcLoad32(unsigned taddr, unsigned (&v)[32]) {
+__device__ __forceinline__ void tcLoad16(unsigned taddr, unsigned (&v)[16]) {
   asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, "
+      "[%16];"
       : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
-        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
-        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
       : "r"(taddr)
       : "memory");
 }
 
-// kind::tf32, FP32 accumulate, A and B K-major, M = 128, N = 32 (bit layout: cute/arch/mma_sm100_desc.hpp)
-constexpr unsigned kTcIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((unsigned)(kTcS >> 3) << 17) | ((128u >> 4) << 24);
+// kind::f16 with FP16 A and B (format 0), FP32 accumulate, A and B K-major, M = 128, N = 32
+// (bit layout: cute/arch/mma_sm100_desc.hpp)
+constexpr unsigned kTcIdesc = (1u << 4) | (0u << 7) | (0u << 10) | ((unsigned)(kTcS >> 3) << 17) | ((128u >> 4) << 24);
+constexpr unsigned kTcHeadMask = 0xFFFFE000u;  // sign, exponent, 10 mantissa bits: an FP16 value when in range
+
+// exponent n of the power of two 2^n that brings a value with |bits| `absBits` into [0.5, 1); 0 for Inf and NaN
+__device__ __forceinline__ int tcScaleExponent(unsigned absBits) {
+  const int e = (int)(absBits >> 23);  // biased exponent; 0 for zero / subnormal: 2^126 keeps those below 1
+  if (e == 255) return 0;
+  const int n = 126 - e;
+  return n < -125 ? -125 : n;
+}
+__device__ __forceinline__ float tcPow2(int n) { return __uint_as_float((unsigned)(n + 127) << 23); }  // -126 <= n <= 127
+
+// mbarWait for the warps that mostly wait (MMA issue, copies): the hardware may suspend the warp for up to `ns` before
+// the try_wait answers, instead of spinning through the issue slots the producers need
+__device__ __forceinline__ void tcWaitRelaxed(unsigned long long* bar, unsigned parity, unsigned ns) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(smemU32(bar)),
+      "r"(parity), "r"(ns)
+      : "memory");
+}
+
+__device__ __forceinline__ unsigned tcPackHalf2(float lo, float hi) {
+  const __half2 p = __floats2half2_rn(lo, hi);
+  return *reinterpret_cast<const unsigned*>(&p);
+}
 
 template <int D, int MINB>
 __global__ void __launch_bounds__(kTcThreads, MINB) firTcKernel(const TcParams P) {
   using G = TcGeom<D>;
   extern __shared__ __align__(16) unsigned char smemRaw[];
-  __shared__ __align__(8) unsigned long long rawFull, rawEmpty, dFull, dEmpty, aFull[kTcRing], aEmpty[kTcRing];
+  __shared__ __align__(8) unsigned long long segFull[G::numSegs], rawEmpty, dFull, dEmpty, aFull[kTcRing], aEmpty[kTcRing];
+  __shared__ int segExp[G::numSegs];  // per segment: the exponent its samples were scaled by
   __shared__ unsigned tmemBaseSlot;
+  __shared__ unsigned redMax[kTcThreads / 32];
   unsigned char* raw = smemRaw;                  // numSegs x segPitch
-  unsigned char* tables = smemRaw + G::rawBytes;  // [hi | lo][numTables][aMax + S] x 16 bytes
+  unsigned char* tables = smemRaw + G::rawBytes;  // [head | remainder][2][aMax + S] x 16 bytes (8 FP16 taps)
 
   const unsigned tid = threadIdx.x, warp = tid >> 5, lane = tid & 31u;
+  constexpr unsigned kMmaWarp = kTcProducers / 32, kNumWarps = kTcThreads / 32;
   if (tid == 0) {
-    mbarInit(&rawFull, 1);
-    mbarInit(&rawEmpty, 128);
+    for (unsigned i = 0; i < G::numSegs; i++) mbarInit(&segFull[i], 1);
+    mbarInit(&rawEmpty, kTcProducers);
     mbarInit(&dFull, 1);
-    mbarInit(&dEmpty, 128);
+    mbarInit(&dEmpty, kTcProducers);
     for (int i = 0; i < kTcRing; i++) {
       mbarInit(&aFull[i], 128);
       mbarInit(&aEmpty[i], 1);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 4) {
+  if (warp == kMmaWarp) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smemU32(&tmemBaseSlot)),
                  "r"(kTcTmemCols)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
-  // tap tables: entry u of table tb holds h[(aMax - u)*D + 4*tb + e], e < 4 (0 outside [0, T)); the hi part is the
-  // tap itself (the tensor core keeps its upper 19 bits), the lo part the exact remainder
+  // tap scale: the largest |h| into [0.5, 1)
+  {
+    unsigned m = 0;
+    for (unsigned i = tid; i < P.T; i += kTcThreads) m = max(m, __float_as_uint(__ldg(P.h + i)) & 0x7fffffffu);
+    m = __reduce_max_sync(0xffffffffu, m);
+    if (lane == 0) redMax[warp] = m;
+  }
+  __syncthreads();
+  unsigned hm = 0;
+  for (unsigned w = 0; w < kNumWarps; w++) hm = max(hm, redMax[w]);
+  const int tapExp = tcScaleExponent(hm);
+  const float tapScale = tcPow2(tapExp);
+  // tap tables: entry u of table tb holds taps (aMax - u)*D + 8*tb + e, e < 8 (0 outside [0, T)), scaled, as FP16 head
+  // and FP16 remainder
   {
     const unsigned entries = P.tablePitch >> 4;
-    const unsigned total = G::numTables * entries * 4u;
-    float* hi = reinterpret_cast<float*>(tables);
-    float* lo = reinterpret_cast<float*>(tables + G::numTables * P.tablePitch);
+    const unsigned total = 2u * entries * 8u;
+    __half* head = reinterpret_cast<__half*>(tables);
+    __half* rem = reinterpret_cast<__half*>(tables + 2u * P.tablePitch);
     for (unsigned i = tid; i < total; i += kTcThreads) {
-      const unsigned e = i & 3u, u = (i >> 2) % entries, tb = (i >> 2) / entries;
-      const long long ti = ((long long)P.aMax - (long long)u) * D + 4 * tb + e;
-      const float v = (ti >= 0 && ti < (long long)P.T) ? __ldg(P.h + ti) : 0.0f;
-      hi[i] = v;
-      lo[i] = v - __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
+      const unsigned e = i & 7u, u = (i >> 3) % entries, tb = (i >> 3) / entries;
+      const long long ti = ((long long)P.aMax - (long long)u) * D + 8 * tb + e;
+      const float v = (ti >= 0 && ti < (long long)P.T) ? __ldg(P.h + ti) * tapScale : 0.0f;
+      const float hd = __uint_as_float(__float_as_uint(v) & kTcHeadMask);
+      head[i] = __float2half_rn(hd);
+      rem[i] = __float2half_rn(v - hd);
     }
   }
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // the tables are read by the tensor core
@@ -181,100 +241,228 @@ __global__ void __launch_bounds__(kTcThreads, MINB) firTcKernel(const TcParams P
   __syncthreads();
   tcFenceAfter();
   const unsigned tmem = tmemBaseSlot;
-  const unsigned colD = 0, colA = kTcS;  // accumulator: 32 columns; A ring: kTcRing x 16 columns
+  // two accumulators of 32 columns (a window's samples in its first / second segment: the segments have their own
+  // scales); A ring: kTcRing x 16 columns
+  const unsigned colD = 0, colA = 2 * kTcS;
+  const bool useSecond = P.numStages * 32u > G::SD;
   const unsigned numStages = P.numStages;
 
-  if (warp < 4) {
+  if (warp < kMmaWarp) {
     // ===================== producers (then epilogue) =====================
-    // lane -> (part, component, window): the four lanes that share a window read the same shared-memory words
-    // (broadcast), and the eight windows of a warp sit in eight different bank groups (16 bytes of segment padding)
-    const unsigned part = lane >> 4;                       // 0: hi part rows, 1: lo part rows
-    const unsigned comp = (lane >> 3) & 1u;                // 0: re, 1: im
-    const unsigned q = 8u * warp + (lane & 7u);            // window of the tile
-    const unsigned mask = part ? 0xFFFFE000u : 0u;         // value = x - (x & mask): x itself, or its low part
-    const unsigned laneAddr = (32u * warp) << 16;
-    unsigned g = 0;  // running stage counter over all tiles of this CTA
+    // lane -> (part, component, window): the eight windows of a warp sit in eight different bank groups (16 bytes of
+    // segment padding), the four rows of a window read four different planes
+    const unsigned group = warp >> 2, quad = warp & 3u;  // warpgroup; TMEM lane quadrant
+    const unsigned part = lane >> 4;                     // 0: head rows, 1: remainder rows
+    const unsigned comp = (lane >> 3) & 1u;              // 0: re, 1: im
+    const unsigned q = 8u * quad + (lane & 7u);          // window of the tile
+    const unsigned laneAddr = (32u * quad) << 16;
+    const unsigned char* row = raw + q * G::segPitch + (2u * comp + part) * G::planeBytes;
+    unsigned g = 0;                 // stage counter over all tiles of this CTA: stage g belongs to warpgroup g & 1
+    unsigned slot = 0, ringPass = 0;  // g % kTcRing, g / kTcRing
     unsigned it = 0;
+#ifdef GSDR_TC_PHASE_TIMING
+    long long ph[6] = {0, 0, 0, 0, 0, 0};
+#define TC_T(n) const long long tc_t##n = clock64()
+#define TC_ACC(i, a, b) ph[i] += tc_t##b - tc_t##a
+#else
+#define TC_T(n)
+#define TC_ACC(i, a, b)
+#endif
     for (unsigned tile = blockIdx.x; tile < P.totalTiles; tile += gridDim.x, it++) {
-      mbarWait(&rawFull, it & 1u);
-      const unsigned char* win = raw + q * G::segPitch + comp * 4u;
-      for (unsigned st = 0; st < numStages; st++, g++) {
-        const unsigned slot = g % kTcRing, n = g / kTcRing;
-        const unsigned k = 16u * st;
-        // samples k .. k+15 of this window: segment q (k < SD) or q + 1
-        const unsigned char* src = win + (k >= G::SD ? G::segPitch + (k - G::SD) * 8u : k * 8u);
-        unsigned v[16];
+      TC_T(0);
+      TC_T(1);
+      TC_T(2);
+      // ---- every segment in place, as it lands: SD complex FP32 -> planes [re head | re rem | im head | im rem] of
+      //      SD FP16, scaled by the power of two that brings the segment's largest |component| into [0.5, 1) ----
+      // one warp per segment; a lane holds chunk 32*p + lane of every pass p before the first plane word is written
+      for (unsigned sg = warp; sg < G::numSegs; sg += kMmaWarp) {
+        unsigned char* seg = raw + sg * G::segPitch;
+        constexpr int kPasses = D / 2;  // SD / 64
+        float4 c[kPasses];
+        mbarWait(&segFull[sg], it & 1u);
+        unsigned m = 0;
 #pragma unroll
-        for (int i = 0; i < 8; i++) {
-          // 16 bytes = samples 2i, 2i+1 (re, im, re, im); comp shifted the base by 4 bytes: .x/.z are ours
-          const float a = *reinterpret_cast<const float*>(src + 16 * i);
-          const float b = *reinterpret_cast<const float*>(src + 16 * i + 8);
-          v[2 * i] = __float_as_uint(a - __uint_as_float(__float_as_uint(a) & mask));
-          v[2 * i + 1] = __float_as_uint(b - __uint_as_float(__float_as_uint(b) & mask));
+        for (int p = 0; p < kPasses; p++) {
+          c[p] = *reinterpret_cast<const float4*>(seg + 16u * (32u * p + lane));
+          m = max(max(m, __float_as_uint(c[p].x) & 0x7fffffffu),
+                  max(max(__float_as_uint(c[p].y) & 0x7fffffffu, __float_as_uint(c[p].z) & 0x7fffffffu),
+                      __float_as_uint(c[p].w) & 0x7fffffffu));
         }
-        if (n > 0) {
-          mbarWait(&aEmpty[slot], (n - 1u) & 1u);  // the MMAs that read this ring slot have completed
-          tcFenceAfter();
+        m = __reduce_max_sync(0xffffffffu, m);  // also orders every lane's loads before the stores below
+        const int xExp = tcScaleExponent(m);
+        const float sx = tcPow2(xExp);
+        if (lane == 0) segExp[sg] = xExp;
+#pragma unroll
+        for (int p = 0; p < kPasses; p++) {
+          const float a = c[p].x * sx, b = c[p].z * sx;  // re of samples 2i, 2i+1
+          const float e = c[p].y * sx, f = c[p].w * sx;  // im
+          const float ah = __uint_as_float(__float_as_uint(a) & kTcHeadMask);
+          const float bh = __uint_as_float(__float_as_uint(b) & kTcHeadMask);
+          const float eh = __uint_as_float(__float_as_uint(e) & kTcHeadMask);
+          const float fh = __uint_as_float(__float_as_uint(f) & kTcHeadMask);
+          unsigned* w = reinterpret_cast<unsigned*>(seg) + 32u * p + lane;
+          w[0] = tcPackHalf2(ah, bh);
+          w[G::planeBytes / 4] = tcPackHalf2(a - ah, b - bh);
+          w[2 * G::planeBytes / 4] = tcPackHalf2(eh, fh);
+          w[3 * G::planeBytes / 4] = tcPackHalf2(e - eh, f - fh);
         }
-        tcStore16(tmem + laneAddr + colA + 16u * slot, v);
-        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-        tcFenceBefore();
-        mbarArrive(&aFull[slot]);
       }
-      mbarArrive(&rawEmpty);  // this thread has no more reads of the raw tile
-      // ---- epilogue: D rows (hi part + lo part) -> y ----
+      asm volatile("bar.sync 1, %0;" ::"n"(kTcProducers) : "memory");  // planes and segExp complete
+      TC_T(3);
+      // ---- stages: 32 samples of this row's plane -> 16 TMEM columns; the warpgroups take alternate stages ----
+      for (unsigned st = 0; st < numStages; st++, g++) {
+        if ((g & 1u) == group) {
+          const unsigned k = 32u * st;
+          const unsigned over = k >= G::SD ? 1u : 0u;  // second segment of the window (stages never straddle)
+          const uint4* src = reinterpret_cast<const uint4*>(row + over * G::segPitch + (k - over * G::SD) * 2u);
+          uint4 v[4];
+#pragma unroll
+          for (int j = 0; j < 4; j++) v[j] = src[j];
+          if (ringPass > 0) {
+            mbarWait(&aEmpty[slot], (ringPass - 1u) & 1u);  // the MMAs that read this ring slot have completed
+            tcFenceAfter();
+          }
+          tcStore16(tmem + laneAddr + colA + 16u * slot, v);
+          asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+          tcFenceBefore();
+          mbarArrive(&aFull[slot]);
+        }
+        if (++slot == kTcRing) {
+          slot = 0;
+          ringPass++;
+        }
+      }
+      TC_T(4);
+      // (read before the arrive: the next tile's conversion rewrites segExp as soon as its copies have landed)
+      const int e1 = -(segExp[q] + tapExp), e2 = -(segExp[q + 1] + tapExp);
+      mbarArrive(&rawEmpty);  // this thread has no more reads of the tile's samples
+      // ---- epilogue: head row + remainder row -> y, undoing both scales (exact powers of two, in two factors to
+      //      stay in range); warpgroup 0 takes the accumulator's columns 0..15, warpgroup 1 columns 16..31 ----
       mbarWait(&dFull, it & 1u);
+      TC_T(5);
       tcFenceAfter();
-      unsigned d[32];
-      tcLoad32(tmem + laneAddr + colD, d);
+      // v[i] = D1[i] / scale(first segment) + D2[i] / scale(second segment), the tap scale undone in the same factors
+      const float f1a = tcPow2(e1 / 2), f1b = tcPow2(e1 - e1 / 2), f2a = tcPow2(e2 / 2), f2b = tcPow2(e2 - e2 / 2);
+      unsigned d[16];
+      float v[16];
+      tcLoad16(tmem + laneAddr + colD + 16u * group, d);
       asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+      for (int i = 0; i < 16; i++) v[i] = (__uint_as_float(d[i]) * f1a) * f1b;
+      if (useSecond) {
+        tcLoad16(tmem + laneAddr + colD + kTcS + 16u * group, d);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+        for (int i = 0; i < 16; i++) v[i] = fmaf(__uint_as_float(d[i]) * f2a, f2b, v[i]);
+      }
       tcFenceBefore();
-      mbarArrive(&dEmpty);  // the accumulator may be overwritten by the next tile
+      mbarArrive(&dEmpty);  // the accumulators may be overwritten by the next tile
+      // the four lanes of a window each end up with four complete outputs: 16*group + 8*part + 4*comp + (0..3).
+      // 1) the two parts trade the half of their columns the other one sums
+      float sum[8];
+#pragma unroll
+      for (int i = 0; i < 8; i++) {
+        const float give = part ? v[i] : v[8 + i];
+        const float keep = part ? v[8 + i] : v[i];
+        sum[i] = keep + __shfl_xor_sync(0xffffffffu, give, 16);
+      }
+      // 2) the two components trade the half of those outputs the other one stores
+      float2 out[4];
+#pragma unroll
+      for (int i = 0; i < 4; i++) {
+        const float give = comp ? sum[i] : sum[4 + i];
+        const float keep = comp ? sum[4 + i] : sum[i];
+        const float got = __shfl_xor_sync(0xffffffffu, give, 8);
+        out[i] = comp ? make_float2(got, keep) : make_float2(keep, got);
+      }
       const unsigned chan = tile / P.tilesPerChannel;
       const unsigned tl = tile - chan * P.tilesPerChannel;
-      const unsigned long long o0 = (unsigned long long)tl * kTcTileOut + q * kTcS;  // first output of the window
-      float* y = reinterpret_cast<float*>(P.y + (size_t)chan * P.yStride + o0) + comp;
-      const unsigned valid = o0 >= P.nOut ? 0u : (P.nOut - o0 >= (unsigned long long)kTcS ? (unsigned)kTcS : (unsigned)(P.nOut - o0));
+      const unsigned long long o0 =
+          (unsigned long long)tl * kTcTileOut + q * kTcS + 16u * group + 8u * part + 4u * comp;
+      float2* y = P.y + (size_t)chan * P.yStride + o0;
+      const unsigned valid = o0 >= P.nOut ? 0u : (P.nOut - o0 >= 4ull ? 4u : (unsigned)(P.nOut - o0));
+      if (valid == 4u && (reinterpret_cast<uintptr_t>(y) & 15u) == 0) {
 #pragma unroll
-      for (int s = 0; s < 32; s++) {
-        const float mine = __uint_as_float(d[s]);
-        const float sum = mine + __shfl_xor_sync(0xffffffffu, mine, 16);
-        // lanes of the hi part store outputs 0..15 of the window, lanes of the lo part outputs 16..31
-        if ((unsigned)(s >> 4) == part && (unsigned)s < valid) y[2 * s] = sum;
+        for (int i = 0; i < 2; i++) {
+          reinterpret_cast<float4*>(y)[i] = make_float4(out[2 * i].x, out[2 * i].y, out[2 * i + 1].x, out[2 * i + 1].y);
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+          if ((unsigned)i < valid) y[i] = out[i];
+        }
       }
+      TC_T(6);
+      TC_ACC(0, 0, 1);
+      TC_ACC(1, 1, 2);
+      TC_ACC(2, 2, 3);
+      TC_ACC(3, 3, 4);
+      TC_ACC(4, 4, 5);
+      TC_ACC(5, 5, 6);
     }
-  } else if (warp == 4) {
+#ifdef GSDR_TC_PHASE_TIMING
+    if ((blockIdx.x == 7 || blockIdx.x == 300) && (tid == 0 || tid == 128)) {
+      printf("tc phases cta %u tid %u tiles %u: rawwait %lld scan %lld convert %lld stages %lld dwait %lld epi %lld (cycles/tile)\n",
+             blockIdx.x, tid, it, ph[0] / it, ph[1] / it, ph[2] / it, ph[3] / it, ph[4] / it, ph[5] / it);
+    }
+#endif
+  } else if (warp == kMmaWarp) {
     // ===================== MMA issue =====================
     const unsigned leader = tcElectOne();
-    const unsigned tabHi = smemU32(tables), tabLo = tabHi + G::numTables * P.tablePitch;
+    const unsigned tabHead = smemU32(tables), tabRem = tabHead + 2u * P.tablePitch;
     const unsigned long long descHigh =
         ((unsigned long long)((128u >> 4) | (1u << 14)) << 32) | ((unsigned long long)((P.tablePitch >> 4) & 0x3FFFu) << 16);
-    unsigned g = 0, it = 0;
+    unsigned slot = 0, ringPass = 0, it = 0;
+#ifdef GSDR_TC_PHASE_TIMING
+    long long mmaWait = 0, mmaIssue = 0;
+#endif
     for (unsigned tile = blockIdx.x; tile < P.totalTiles; tile += gridDim.x, it++) {
       if (it > 0) {
-        mbarWait(&dEmpty, (it - 1u) & 1u);  // the epilogue has read the previous tile's accumulator
+        tcWaitRelaxed(&dEmpty, (it - 1u) & 1u, 200);  // the epilogue has read the previous tile's accumulator
         tcFenceAfter();
       }
-      for (unsigned st = 0; st < numStages; st++, g++) {
-        const unsigned slot = g % kTcRing, n = g / kTcRing;
-        mbarWait(&aFull[slot], n & 1u);
+      for (unsigned st = 0; st < numStages; st++) {
+#ifdef GSDR_TC_PHASE_TIMING
+        const long long mA = clock64();
+#endif
+        tcWaitRelaxed(&aFull[slot], ringPass & 1u, 200);
+#ifdef GSDR_TC_PHASE_TIMING
+        const long long mB = clock64();
+#endif
         tcFenceAfter();
         if (leader) {
 #pragma unroll
           for (unsigned half = 0; half < 2; half++) {
-            const unsigned j = 2u * st + half;           // k-step: k = 8j .. 8j+7
-            const unsigned a = (8u * j) / D, tb0 = ((8u * j) % D) / 4u;
-            const unsigned off = tb0 * P.tablePitch + 16u * (P.aMax - a);
+            const unsigned j = 2u * st + half;  // k-step: k = 16j .. 16j+15
+            const unsigned a = (16u * j) / D;   // tap-row offset of the step's first sample
+            const unsigned off = 16u * (P.aMax - a);
             const unsigned aCols = tmem + colA + 16u * slot + 8u * half;
-            tcMma(tmem + colD, aCols, descHigh | (((tabHi + off) >> 4) & 0x3FFFu), kTcIdesc, j > 0 ? 1u : 0u);
-            tcMma(tmem + colD, aCols, descHigh | (((tabLo + off) >> 4) & 0x3FFFu), kTcIdesc, 1u);
+            const unsigned second = 16u * j >= G::SD ? 1u : 0u;  // the window's second segment: second accumulator
+            const unsigned acc = tmem + colD + second * kTcS;
+            const unsigned first = (j == 0 || 16u * j == G::SD) ? 0u : 1u;
+            tcMmaF16(acc, aCols, descHigh | (((tabHead + off) >> 4) & 0x3FFFu), kTcIdesc, first);
+            tcMmaF16(acc, aCols, descHigh | (((tabRem + off) >> 4) & 0x3FFFu), kTcIdesc, 1u);
           }
           tcCommit(&aEmpty[slot]);
           if (st + 1 == numStages) tcCommit(&dFull);
         }
         __syncwarp();
+#ifdef GSDR_TC_PHASE_TIMING
+        mmaWait += mB - mA;
+        mmaIssue += clock64() - mB;
+#endif
+        if (++slot == kTcRing) {
+          slot = 0;
+          ringPass++;
+        }
       }
     }
+#ifdef GSDR_TC_PHASE_TIMING
+    if ((blockIdx.x == 7 || blockIdx.x == 300) && lane == 0) {
+      printf("tc mma warp cta %u tiles %u: wait aFull %lld issue %lld (cycles/tile)\n", blockIdx.x, it, mmaWait / it,
+             mmaIssue / it);
+    }
+#endif
   } else {
     // ===================== copy warp: 33 segments per tile =====================
     unsigned it = 0;
@@ -283,34 +471,35 @@ __global__ void __launch_bounds__(kTcThreads, MINB) firTcKernel(const TcParams P
       const unsigned tl = tile - chan * P.tilesPerChannel;
       const float2* src = P.x + (size_t)chan * P.xStride;
       const unsigned long long s0 = (unsigned long long)tl * kTcTileOut * D;  // first sample of the tile
-      if (it > 0) mbarWait(&rawEmpty, (it - 1u) & 1u);  // every producer has left the previous tile's samples
-      // segments inside the caller-guaranteed extent: one bulk copy each; the others: guarded loads, zero fill
+      if (it > 0) tcWaitRelaxed(&rawEmpty, (it - 1u) & 1u, 500);  // every producer has left the previous tile's samples
+      // segments inside the caller-guaranteed extent (a prefix): one bulk copy each, every one on its own barrier so
+      // that its conversion starts when it lands; the others: guarded loads, zero fill
       unsigned fast = 0;
       for (unsigned sg = 0; sg < G::numSegs; sg++) {
-        const unsigned long long b = s0 + (unsigned long long)sg * G::SD;
-        if (b + G::SD <= P.nIn) {
-          fast++;
-        } else {
-          float2* dst = reinterpret_cast<float2*>(raw + sg * G::segPitch);
-          for (unsigned i = lane; i < G::SD; i += 32) {
-            dst[i] = (b + i < P.nIn) ? __ldg(src + b + i) : make_float2(0.0f, 0.0f);
-          }
-        }
+        if (s0 + (unsigned long long)(sg + 1u) * G::SD <= P.nIn) fast++;
       }
-      __syncwarp();
       if (lane == 0) {
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        mbarExpectTx(&rawFull, fast * G::segBytes);  // also the one arrival the barrier waits for
-        for (unsigned sg = 0; sg < fast; sg++) {     // in-bounds segments form a prefix
-          bulkLoad1d(raw + sg * G::segPitch, src + s0 + (size_t)sg * G::SD, G::segBytes, &rawFull);
+        for (unsigned sg = 0; sg < fast; sg++) {
+          mbarExpectTx(&segFull[sg], G::segBytes);  // also the one arrival the barrier waits for
+          bulkLoad1d(raw + sg * G::segPitch, src + s0 + (size_t)sg * G::SD, G::segBytes, &segFull[sg]);
         }
+      }
+      for (unsigned sg = fast; sg < G::numSegs; sg++) {
+        const unsigned long long b = s0 + (unsigned long long)sg * G::SD;
+        float2* dst = reinterpret_cast<float2*>(raw + sg * G::segPitch);
+        for (unsigned i = lane; i < G::SD; i += 32) {
+          dst[i] = (b + i < P.nIn) ? __ldg(src + b + i) : make_float2(0.0f, 0.0f);
+        }
+        __syncwarp();
+        if (lane == 0) mbarArrive(&segFull[sg]);
       }
       __syncwarp();
     }
   }
   tcFenceBefore();
   __syncthreads();
-  if (warp == 4) {
+  if (warp == kMmaWarp) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(kTcTmemCols) : "memory");
   }
 }

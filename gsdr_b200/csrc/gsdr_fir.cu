@@ -794,7 +794,7 @@ static cudaError_t launchDirectNco(const FirCall& c, cudaStream_t stream) noexce
 static size_t outElemBytes(FirType t) noexcept { return t == kFirFF ? 4 : 8; }
 
 // ---------------------------------------------------------------------------------------------------------
-// Tensor-core path (fir_tc_kernel.cuh): FC, decimation 4 / 8 / 16, about 32 taps per output
+// Tensor-core path (fir_tc_kernel.cuh): FC, decimation 4 / 8 / 16, up to 33 taps per output
 // ---------------------------------------------------------------------------------------------------------
 #ifdef GSDR_B200_TUNING
 size_t tcSharedBytes(unsigned D, unsigned tablePitch) noexcept;
@@ -815,8 +815,8 @@ static unsigned long long tcTilesPerChannel(const FirCall& c, int maxSmem, TcPar
   const unsigned long long tiles = (c.numOutputs + kTcTileOut - 1) / kTcTileOut;
   if (tiles * c.numChannels > 0x7fffffffull) return 0;
   const unsigned K = (unsigned)((kTcS - 1) * D + T);
-  P->numStages = (K + 15u) / 16u;
-  P->aMax = (8u * (2u * P->numStages - 1u)) / (unsigned)D;
+  P->numStages = (K + 31u) / 32u;
+  P->aMax = (16u * (2u * P->numStages - 1u)) / (unsigned)D;
   P->tablePitch = (P->aMax + kTcS) * 16u;
   if (tcSharedBytes((unsigned)D, P->tablePitch) > (size_t)maxSmem) return 0;
   return tiles;
