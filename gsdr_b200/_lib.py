@@ -13,7 +13,7 @@ from pathlib import Path
 LIB_PATH = Path(os.environ.get("GSDR_B200_LIB") or Path(__file__).resolve().parent / "csrc" / "libgsdr_b200.so")
 # The tuning build (-DGSDR_B200_TUNING): same code plus gsdrB200SetKernelVariant / gsdrB200SetDebugFlags.  Loaded on
 # demand by api.set_kernel_variant / api.set_debug_flags (variant-coverage tests, tools/sweep.py) — never by default.
-TUNING_LIB_PATH = Path(__file__).resolve().parent / "csrc" / "libgsdr_b200_tuning.so"
+TUNING_LIB_PATH = Path(os.environ.get("GSDR_B200_TUNING_LIB") or Path(__file__).resolve().parent / "csrc" / "libgsdr_b200_tuning.so")
 
 c_size_t = C.c_size_t
 c_void_p = C.c_void_p

@@ -76,7 +76,12 @@ struct TcParams {
 constexpr int kTcS = 32;          // outputs per window = MMA N
 constexpr int kTcWindows = 32;    // windows per tile
 constexpr int kTcTileOut = kTcS * kTcWindows;
-constexpr int kTcRing = 4;        // TMEM stages of 16 columns (next to two accumulators of 32)
+#ifndef GSDR_TC_EXPERIMENT
+#define GSDR_TC_EXPERIMENT 0
+#endif
+// TMEM stages of 16 columns, next to the two accumulators of 32.  (Two more stages in a second allocation of 32
+// columns were measured: 3 % slower — the ring is not what the stage loop waits for.)
+constexpr int kTcRing = 4;
 constexpr int kTcProducers = 256;  // warps 0-7: two warpgroups of producers + epilogue (warp w and w + 4 share the
                                    // TMEM lanes 32 * (w & 3) ..: the groups take alternate stages)
 constexpr int kTcThreads = kTcProducers + 64;  // warp 8: MMA issue, warp 9: bulk copies
@@ -157,20 +162,29 @@ __device__ __forceinline__ int tcScaleExponent(unsigned absBits) {
 }
 __device__ __forceinline__ float tcPow2(int n) { return __uint_as_float((unsigned)(n + 127) << 23); }  // -126 <= n <= 127
 
-// mbarWait for the warps that mostly wait (MMA issue, copies): the hardware may suspend the warp for up to `ns` before
-// the try_wait answers, instead of spinning through the issue slots the producers need
-__device__ __forceinline__ void tcWaitRelaxed(unsigned long long* bar, unsigned parity, unsigned ns) {
+// The kernel is capped at 64 registers (three CTAs of ten warps per SM) and ptxas would rather recompute thread ids and
+// shared-window addresses inside the stage loop (S2R / S2UR + address arithmetic on the critical path of every stage)
+// than keep them: values passed through here are opaque to it and stay in their register.
+__device__ __forceinline__ unsigned tcKeep(unsigned v) {
+  unsigned r;
+  asm volatile("mov.u32 %0, %1;" : "=r"(r) : "r"(v));
+  return r;
+}
+__device__ __forceinline__ void tcBarWait(unsigned barAddr, unsigned parity) {
   asm volatile(
       "{\n"
       ".reg .pred p;\n"
       "WAIT_%=:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
       "@p bra DONE_%=;\n"
       "bra WAIT_%=;\n"
       "DONE_%=:\n"
-      "}\n" ::"r"(smemU32(bar)),
-      "r"(parity), "r"(ns)
+      "}\n" ::"r"(barAddr),
+      "r"(parity)
       : "memory");
+}
+__device__ __forceinline__ void tcBarArrive(unsigned barAddr) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(barAddr) : "memory");
 }
 
 __device__ __forceinline__ unsigned tcPackHalf2(float lo, float hi) {
@@ -189,7 +203,7 @@ __global__ void __launch_bounds__(kTcThreads, MINB) firTcKernel(const TcParams P
   unsigned char* raw = smemRaw;                  // numSegs x segPitch
   unsigned char* tables = smemRaw + G::rawBytes;  // [head | remainder][2][aMax + S] x 16 bytes (8 FP16 taps)
 
-  const unsigned tid = threadIdx.x, warp = tid >> 5, lane = tid & 31u;
+  const unsigned tid = tcKeep(threadIdx.x), warp = tid >> 5, lane = tid & 31u;
   constexpr unsigned kMmaWarp = kTcProducers / 32, kNumWarps = kTcThreads / 32;
   if (tid == 0) {
     for (unsigned i = 0; i < G::numSegs; i++) mbarInit(&segFull[i], 1);
@@ -241,9 +255,10 @@ __global__ void __launch_bounds__(kTcThreads, MINB) firTcKernel(const TcParams P
   __syncthreads();
   tcFenceAfter();
   const unsigned tmem = tmemBaseSlot;
+  auto slotCols = [&](unsigned slot) { return tmem + 2u * kTcS + 16u * slot; };
   // two accumulators of 32 columns (a window's samples in its first / second segment: the segments have their own
   // scales); A ring: kTcRing x 16 columns
-  const unsigned colD = 0, colA = 2 * kTcS;
+  const unsigned colD = 0;
   const bool useSecond = P.numStages * 32u > G::SD;
   const unsigned numStages = P.numStages;
 
@@ -255,10 +270,11 @@ __global__ void __launch_bounds__(kTcThreads, MINB) firTcKernel(const TcParams P
     const unsigned part = lane >> 4;                     // 0: head rows, 1: remainder rows
     const unsigned comp = (lane >> 3) & 1u;              // 0: re, 1: im
     const unsigned q = 8u * quad + (lane & 7u);          // window of the tile
-    const unsigned laneAddr = (32u * quad) << 16;
+    const unsigned laneAddr = tcKeep((32u * quad) << 16);
+    const unsigned aFullAddr = tcKeep(smemU32(&aFull[0])), aEmptyAddr = tcKeep(smemU32(&aEmpty[0]));
+    const unsigned ringBase = tcKeep(tmem + 2u * kTcS + laneAddr);
     const unsigned char* row = raw + q * G::segPitch + (2u * comp + part) * G::planeBytes;
     unsigned g = 0;                 // stage counter over all tiles of this CTA: stage g belongs to warpgroup g & 1
-    unsigned slot = 0, ringPass = 0;  // g % kTcRing, g / kTcRing
     unsigned it = 0;
 #ifdef GSDR_TC_PHASE_TIMING
     long long ph[6] = {0, 0, 0, 0, 0, 0};
@@ -280,15 +296,15 @@ __global__ void __launch_bounds__(kTcThreads, MINB) firTcKernel(const TcParams P
         constexpr int kPasses = D / 2;  // SD / 64
         float4 c[kPasses];
         mbarWait(&segFull[sg], it & 1u);
-        unsigned m = 0;
+        // the largest |component| (fmaxf drops NaNs: a NaN stays a NaN under any scale; an Inf gives scale 1)
+        float mf = 0.0f;
 #pragma unroll
         for (int p = 0; p < kPasses; p++) {
           c[p] = *reinterpret_cast<const float4*>(seg + 16u * (32u * p + lane));
-          m = max(max(m, __float_as_uint(c[p].x) & 0x7fffffffu),
-                  max(max(__float_as_uint(c[p].y) & 0x7fffffffu, __float_as_uint(c[p].z) & 0x7fffffffu),
-                      __float_as_uint(c[p].w) & 0x7fffffffu));
+          mf = fmaxf(fmaxf(mf, fabsf(c[p].x)), fmaxf(fmaxf(fabsf(c[p].y), fabsf(c[p].z)), fabsf(c[p].w)));
         }
-        m = __reduce_max_sync(0xffffffffu, m);  // also orders every lane's loads before the stores below
+        // (the reduction also orders every lane's loads before the stores below)
+        const unsigned m = __reduce_max_sync(0xffffffffu, __float_as_uint(mf));
         const int xExp = tcScaleExponent(m);
         const float sx = tcPow2(xExp);
         if (lane == 0) segExp[sg] = xExp;
@@ -310,28 +326,42 @@ __global__ void __launch_bounds__(kTcThreads, MINB) firTcKernel(const TcParams P
       asm volatile("bar.sync 1, %0;" ::"n"(kTcProducers) : "memory");  // planes and segExp complete
       TC_T(3);
       // ---- stages: 32 samples of this row's plane -> 16 TMEM columns; the warpgroups take alternate stages ----
-      for (unsigned st = 0; st < numStages; st++, g++) {
-        if ((g & 1u) == group) {
-          const unsigned k = 32u * st;
-          const unsigned over = k >= G::SD ? 1u : 0u;  // second segment of the window (stages never straddle)
-          const uint4* src = reinterpret_cast<const uint4*>(row + over * G::segPitch + (k - over * G::SD) * 2u);
-          uint4 v[4];
+      // a warp's own stages are st0, st0 + 2, ...; the loads of its next stage are in flight while the tcgen05.st of
+      // the current one completes
+      auto stageSrc = [&](unsigned st) {
+        const unsigned k = 32u * st;
+        const unsigned over = k >= G::SD ? 1u : 0u;  // second segment of the window (stages never straddle)
+        return reinterpret_cast<const uint4*>(row + over * G::segPitch + (k - over * G::SD) * 2u);
+      };
+      const unsigned st0 = (g ^ group) & 1u;
+      unsigned slot = (g + st0) % kTcRing, ringPass = (g + st0) / kTcRing;
+      uint4 av[4];
+      if (st0 < numStages) {
+        const uint4* src = stageSrc(st0);
 #pragma unroll
-          for (int j = 0; j < 4; j++) v[j] = src[j];
-          if (ringPass > 0) {
-            mbarWait(&aEmpty[slot], (ringPass - 1u) & 1u);  // the MMAs that read this ring slot have completed
-            tcFenceAfter();
-          }
-          tcStore16(tmem + laneAddr + colA + 16u * slot, v);
-          asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-          tcFenceBefore();
-          mbarArrive(&aFull[slot]);
+        for (int j = 0; j < 4; j++) av[j] = src[j];
+      }
+      for (unsigned st = st0; st < numStages; st += 2) {
+        if (ringPass > 0) {
+          tcBarWait(aEmptyAddr + 8u * slot, (ringPass - 1u) & 1u);  // the MMAs that read this slot have completed
+          tcFenceAfter();
         }
-        if (++slot == kTcRing) {
-          slot = 0;
+        tcStore16(ringBase + 16u * slot, av);
+        if (st + 2 < numStages) {
+          const uint4* src = stageSrc(st + 2);
+#pragma unroll
+          for (int j = 0; j < 4; j++) av[j] = src[j];
+        }
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        tcFenceBefore();
+        tcBarArrive(aFullAddr + 8u * slot);
+        slot += 2;
+        if (slot >= kTcRing) {
+          slot -= kTcRing;
           ringPass++;
         }
       }
+      g += numStages;
       TC_T(4);
       // (read before the arrive: the next tile's conversion rewrites segExp as soon as its copies have landed)
       const int e1 = -(segExp[q] + tapExp), e2 = -(segExp[q + 1] + tapExp);
@@ -418,14 +448,14 @@ __global__ void __launch_bounds__(kTcThreads, MINB) firTcKernel(const TcParams P
 #endif
     for (unsigned tile = blockIdx.x; tile < P.totalTiles; tile += gridDim.x, it++) {
       if (it > 0) {
-        tcWaitRelaxed(&dEmpty, (it - 1u) & 1u, 200);  // the epilogue has read the previous tile's accumulator
+        mbarWait(&dEmpty, (it - 1u) & 1u);  // the epilogue has read the previous tile's accumulators
         tcFenceAfter();
       }
       for (unsigned st = 0; st < numStages; st++) {
 #ifdef GSDR_TC_PHASE_TIMING
         const long long mA = clock64();
 #endif
-        tcWaitRelaxed(&aFull[slot], ringPass & 1u, 200);
+        mbarWait(&aFull[slot], ringPass & 1u);  // (a suspended wait costs 4 % here: the ring is latency-bound)
 #ifdef GSDR_TC_PHASE_TIMING
         const long long mB = clock64();
 #endif
@@ -436,12 +466,19 @@ __global__ void __launch_bounds__(kTcThreads, MINB) firTcKernel(const TcParams P
             const unsigned j = 2u * st + half;  // k-step: k = 16j .. 16j+15
             const unsigned a = (16u * j) / D;   // tap-row offset of the step's first sample
             const unsigned off = 16u * (P.aMax - a);
-            const unsigned aCols = tmem + colA + 16u * slot + 8u * half;
+            const unsigned aCols = slotCols(slot) + 8u * half;
             const unsigned second = 16u * j >= G::SD ? 1u : 0u;  // the window's second segment: second accumulator
             const unsigned acc = tmem + colD + second * kTcS;
             const unsigned first = (j == 0 || 16u * j == G::SD) ? 0u : 1u;
+#if GSDR_TC_EXPERIMENT == 2
+            tcMmaF16(acc, aCols, descHigh | (((tabHead + off) >> 4) & 0x3FFFu),
+                     (kTcIdesc & ~(0x3fu << 17)) | ((64u >> 3) << 17), first);
+#else
             tcMmaF16(acc, aCols, descHigh | (((tabHead + off) >> 4) & 0x3FFFu), kTcIdesc, first);
+#endif
+#if !GSDR_TC_EXPERIMENT
             tcMmaF16(acc, aCols, descHigh | (((tabRem + off) >> 4) & 0x3FFFu), kTcIdesc, 1u);
+#endif
           }
           tcCommit(&aEmpty[slot]);
           if (st + 1 == numStages) tcCommit(&dFull);
@@ -471,13 +508,13 @@ __global__ void __launch_bounds__(kTcThreads, MINB) firTcKernel(const TcParams P
       const unsigned tl = tile - chan * P.tilesPerChannel;
       const float2* src = P.x + (size_t)chan * P.xStride;
       const unsigned long long s0 = (unsigned long long)tl * kTcTileOut * D;  // first sample of the tile
-      if (it > 0) tcWaitRelaxed(&rawEmpty, (it - 1u) & 1u, 500);  // every producer has left the previous tile's samples
+      if (it > 0) mbarWait(&rawEmpty, (it - 1u) & 1u);  // every producer has left the previous tile's samples  // every producer has left the previous tile's samples
       // segments inside the caller-guaranteed extent (a prefix): one bulk copy each, every one on its own barrier so
       // that its conversion starts when it lands; the others: guarded loads, zero fill
-      unsigned fast = 0;
-      for (unsigned sg = 0; sg < G::numSegs; sg++) {
-        if (s0 + (unsigned long long)(sg + 1u) * G::SD <= P.nIn) fast++;
-      }
+      const unsigned long long room = P.nIn > s0 ? (P.nIn - s0) / G::SD : 0ull;
+      const unsigned fast = room < G::numSegs ? (unsigned)room : G::numSegs;
+      // (one lane issues all the copies, in segment order: 32 lanes issuing one each was measured 7 % slower — the
+      // segments then land out of order and the conversion, which takes them in order, starts late)
       if (lane == 0) {
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         for (unsigned sg = 0; sg < fast; sg++) {
