@@ -246,6 +246,10 @@ class Ctx:
 
 
 def _kernel_text(g, info) -> str:
+    if info.variant == g.num_kernel_variants():
+        return (f"tensor-core kernel (tcgen05.mma kind::f16, FP16 head + remainder operands, FP32 accumulators in "
+                f"TMEM; gsdr_b200/csrc/fir_tc_kernel.cuh): {info.threadsPerBlock} threads/CTA, "
+                f"{info.outputsPerBlock} outputs/tile, {info.sharedBytesPerBlock} B smem, {info.numBlocks} tiles")
     fam = "TMA-fed" if info.variant >= g.num_polyphase_variants() else "cp.async-staged"
     return (f"{fam} persistent polyphase kernel, variant {info.variant}: {info.threadsPerBlock} threads/CTA, "
             f"{info.outputsPerThread} outputs/thread, {info.phaseGroups} branch groups, {info.sharedBytesPerBlock} B "
@@ -289,10 +293,11 @@ def case_fc(c: Ctx, name: str, steps: int, warmup: int, keep=False) -> dict:
             traffic = json.loads(tp.read_text()).get(name)
         except Exception:
             traffic = None
-    roof = bl.roofline(8 * sh.numInputs + 8 * sh.numOutputs + 4 * T, 4.0 * T * sh.numOutputs, mine * 1e-3,
-                       c.fp32_peak, c.fp32_src, traffic)
-    roof["fp32"]["ffma_tflops"], roof["fp32"]["ffma2_tflops"] = c.ffma_tf, c.ffma2_tf
     info = g.describe_kernel(4 if wl["nco"] else 0, D, T, sh.numOutputs, c.local)
+    on_tensor_cores = info.variant == g.num_kernel_variants()
+    roof = bl.roofline(8 * sh.numInputs + 8 * sh.numOutputs + 4 * T, 4.0 * T * sh.numOutputs, mine * 1e-3,
+                       c.fp32_peak, c.fp32_src, traffic, tensor_core=on_tensor_cores)
+    roof["fp32"]["ffma_tflops"], roof["fp32"]["ffma2_tflops"] = c.ffma_tf, c.ffma2_tf
     out = {"ms_per_step": ms, "value": n_in_total / (ms * 1e-3) / 1e6, "unit": UNIT, "scaling": "weak",
            "roofline": roof, "parity": parity, "clocks": clocks, "gpu_launches": steps, "kernel": _kernel_text(g, info),
            "config": bl.config_block(name, c.world)}

@@ -141,6 +141,7 @@ SIGNATURES = {
     "gsdrB200NumKernelVariants": (C.c_int, []),
     "gsdrB200NumPolyphaseVariants": (C.c_int, []),
     "gsdrB200HasTuningHooks": (C.c_int, []),
+    "gsdrB200SetFirTensorCores": (C.c_int, [C.c_int]),
 }
 
 # exported by the tuning build only (include/gsdr/b200.h, #ifdef GSDR_B200_TUNING)

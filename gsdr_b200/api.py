@@ -219,6 +219,16 @@ def set_debug_flags(flags: int) -> None:
         _lib.tuning_lib().gsdrB200SetDebugFlags(flags)
 
 
+def set_fir_tensor_cores(enable: bool) -> bool:
+    """gsdrB200SetFirTensorCores: False keeps every FIR call on the FFMA2 kernels.  Applies to both loaded builds;
+    returns the previous setting."""
+    prev = bool(L().gsdrB200SetFirTensorCores(1 if enable else 0))
+    for other in (_lib.lib, _lib._tuning):
+        if other is not None and other is not L():
+            other.gsdrB200SetFirTensorCores(1 if enable else 0)
+    return prev
+
+
 def has_tuning_hooks() -> bool:
     return bool(L().gsdrB200HasTuningHooks())
 

@@ -1,7 +1,5 @@
 // fir_inst_tc.cu — kernel instantiations and launcher of the tensor-core FIR (fir_tc_kernel.cuh).
-// Compiled into the tuning build only (DESIGN.md §4.3b holds the measurements and the decision).
-#ifdef GSDR_B200_TUNING
-// #define GSDR_TC_PHASE_TIMING 1   // per-phase cycle counts of two CTAs, printed by the kernel (diagnosis only)
+// (DESIGN.md §4.3b holds the measurements and the decision where it is used.)
 #include <atomic>
 #include <cstdio>
 #include <cstdlib>
@@ -27,9 +25,6 @@ static cudaError_t launchTcT(TcParams& P, size_t smem, int dev, int smCount, cud
     cudaError_t st = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, kernel, kTcThreads, configured[dev & 63].load());
     if (st != cudaSuccess) return report(st, "cudaOccupancyMaxActiveBlocksPerMultiprocessor");
     if (perSm < 1) return cudaErrorInvalidConfiguration;
-    if (const char* dbg = std::getenv("GSDR_TC_DEBUG")) {
-      std::fprintf(stderr, "gsdr-b200: firTcKernel<%d> occupancy query: %d CTAs/SM for %zu B (%s)\n", D, perSm, smem, dbg);
-    }
     // the occupancy query has been seen to answer 1 for this kernel; shared memory is what really limits it
     int smemPerSm = 0;
     if (cudaDeviceGetAttribute(&smemPerSm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev) == cudaSuccess) {
@@ -63,4 +58,3 @@ cudaError_t launchTc(unsigned D, TcParams& P, int dev, int smCount, cudaStream_t
 }
 
 }  // namespace gsdr_b200
-#endif  // GSDR_B200_TUNING

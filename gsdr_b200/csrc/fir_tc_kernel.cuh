@@ -76,9 +76,6 @@ struct TcParams {
 constexpr int kTcS = 32;          // outputs per window = MMA N
 constexpr int kTcWindows = 32;    // windows per tile
 constexpr int kTcTileOut = kTcS * kTcWindows;
-#ifndef GSDR_TC_EXPERIMENT
-#define GSDR_TC_EXPERIMENT 0
-#endif
 // TMEM stages of 16 columns, next to the two accumulators of 32.  (Two more stages in a second allocation of 32
 // columns were measured: 3 % slower — the ring is not what the stage loop waits for.)
 constexpr int kTcRing = 4;
@@ -274,33 +271,36 @@ __global__ void __launch_bounds__(kTcThreads, MINB) firTcKernel(const TcParams P
     const unsigned aFullAddr = tcKeep(smemU32(&aFull[0])), aEmptyAddr = tcKeep(smemU32(&aEmpty[0]));
     const unsigned ringBase = tcKeep(tmem + 2u * kTcS + laneAddr);
     const unsigned char* row = raw + q * G::segPitch + (2u * comp + part) * G::planeBytes;
+    const unsigned lastSegValid = P.T > (unsigned)D ? P.T - (unsigned)D : 0u;  // (S-1)*D + T - S*D
     unsigned g = 0;                 // stage counter over all tiles of this CTA: stage g belongs to warpgroup g & 1
     unsigned it = 0;
-#ifdef GSDR_TC_PHASE_TIMING
-    long long ph[6] = {0, 0, 0, 0, 0, 0};
-#define TC_T(n) const long long tc_t##n = clock64()
-#define TC_ACC(i, a, b) ph[i] += tc_t##b - tc_t##a
-#else
-#define TC_T(n)
-#define TC_ACC(i, a, b)
-#endif
     for (unsigned tile = blockIdx.x; tile < P.totalTiles; tile += gridDim.x, it++) {
-      TC_T(0);
-      TC_T(1);
-      TC_T(2);
       // ---- every segment in place, as it lands: SD complex FP32 -> planes [re head | re rem | im head | im rem] of
       //      SD FP16, scaled by the power of two that brings the segment's largest |component| into [0.5, 1) ----
-      // one warp per segment; a lane holds chunk 32*p + lane of every pass p before the first plane word is written
+      // one warp per segment (taking them from a shared counter instead, 33 over 8 warps, measured 1 % slower); a
+      // lane holds chunk 32*p + lane of every pass p before the first plane word is written
       for (unsigned sg = warp; sg < G::numSegs; sg += kMmaWarp) {
         unsigned char* seg = raw + sg * G::segPitch;
         constexpr int kPasses = D / 2;  // SD / 64
         float4 c[kPasses];
         mbarWait(&segFull[sg], it & 1u);
         // the largest |component| (fmaxf drops NaNs: a NaN stays a NaN under any scale; an Inf gives scale 1)
+#pragma unroll
+        for (int p = 0; p < kPasses; p++) c[p] = *reinterpret_cast<const float4*>(seg + 16u * (32u * p + lane));
+        if (sg == G::numSegs - 1u) {
+          // the tile's last segment serves the last window only, which reads its first T - D samples: the others (the
+          // next tile's, or nothing at the end of a call) must not set the scale — that is what makes a tile's
+          // results a function of the tile's own samples, and aligned time shards bit-identical to the whole call
+#pragma unroll
+          for (int p = 0; p < kPasses; p++) {
+            const unsigned i0 = 2u * (32u * p + lane);
+            if (i0 >= lastSegValid) c[p].x = c[p].y = 0.0f;
+            if (i0 + 1u >= lastSegValid) c[p].z = c[p].w = 0.0f;
+          }
+        }
         float mf = 0.0f;
 #pragma unroll
         for (int p = 0; p < kPasses; p++) {
-          c[p] = *reinterpret_cast<const float4*>(seg + 16u * (32u * p + lane));
           mf = fmaxf(fmaxf(mf, fabsf(c[p].x)), fmaxf(fmaxf(fabsf(c[p].y), fabsf(c[p].z)), fabsf(c[p].w)));
         }
         // (the reduction also orders every lane's loads before the stores below)
@@ -324,7 +324,6 @@ __global__ void __launch_bounds__(kTcThreads, MINB) firTcKernel(const TcParams P
         }
       }
       asm volatile("bar.sync 1, %0;" ::"n"(kTcProducers) : "memory");  // planes and segExp complete
-      TC_T(3);
       // ---- stages: 32 samples of this row's plane -> 16 TMEM columns; the warpgroups take alternate stages ----
       // a warp's own stages are st0, st0 + 2, ...; the loads of its next stage are in flight while the tcgen05.st of
       // the current one completes
@@ -362,14 +361,12 @@ __global__ void __launch_bounds__(kTcThreads, MINB) firTcKernel(const TcParams P
         }
       }
       g += numStages;
-      TC_T(4);
       // (read before the arrive: the next tile's conversion rewrites segExp as soon as its copies have landed)
       const int e1 = -(segExp[q] + tapExp), e2 = -(segExp[q + 1] + tapExp);
       mbarArrive(&rawEmpty);  // this thread has no more reads of the tile's samples
       // ---- epilogue: head row + remainder row -> y, undoing both scales (exact powers of two, in two factors to
       //      stay in range); warpgroup 0 takes the accumulator's columns 0..15, warpgroup 1 columns 16..31 ----
       mbarWait(&dFull, it & 1u);
-      TC_T(5);
       tcFenceAfter();
       // v[i] = D1[i] / scale(first segment) + D2[i] / scale(second segment), the tap scale undone in the same factors
       const float f1a = tcPow2(e1 / 2), f1b = tcPow2(e1 - e1 / 2), f2a = tcPow2(e2 / 2), f2b = tcPow2(e2 - e2 / 2);
@@ -422,20 +419,7 @@ __global__ void __launch_bounds__(kTcThreads, MINB) firTcKernel(const TcParams P
           if ((unsigned)i < valid) y[i] = out[i];
         }
       }
-      TC_T(6);
-      TC_ACC(0, 0, 1);
-      TC_ACC(1, 1, 2);
-      TC_ACC(2, 2, 3);
-      TC_ACC(3, 3, 4);
-      TC_ACC(4, 4, 5);
-      TC_ACC(5, 5, 6);
     }
-#ifdef GSDR_TC_PHASE_TIMING
-    if ((blockIdx.x == 7 || blockIdx.x == 300) && (tid == 0 || tid == 128)) {
-      printf("tc phases cta %u tid %u tiles %u: rawwait %lld scan %lld convert %lld stages %lld dwait %lld epi %lld (cycles/tile)\n",
-             blockIdx.x, tid, it, ph[0] / it, ph[1] / it, ph[2] / it, ph[3] / it, ph[4] / it, ph[5] / it);
-    }
-#endif
   } else if (warp == kMmaWarp) {
     // ===================== MMA issue =====================
     const unsigned leader = tcElectOne();
@@ -443,22 +427,14 @@ __global__ void __launch_bounds__(kTcThreads, MINB) firTcKernel(const TcParams P
     const unsigned long long descHigh =
         ((unsigned long long)((128u >> 4) | (1u << 14)) << 32) | ((unsigned long long)((P.tablePitch >> 4) & 0x3FFFu) << 16);
     unsigned slot = 0, ringPass = 0, it = 0;
-#ifdef GSDR_TC_PHASE_TIMING
-    long long mmaWait = 0, mmaIssue = 0;
-#endif
     for (unsigned tile = blockIdx.x; tile < P.totalTiles; tile += gridDim.x, it++) {
       if (it > 0) {
+        __nanosleep(500);  // the next tile's first stage is further away than that (copies, conversion)
         mbarWait(&dEmpty, (it - 1u) & 1u);  // the epilogue has read the previous tile's accumulators
         tcFenceAfter();
       }
       for (unsigned st = 0; st < numStages; st++) {
-#ifdef GSDR_TC_PHASE_TIMING
-        const long long mA = clock64();
-#endif
         mbarWait(&aFull[slot], ringPass & 1u);  // (a suspended wait costs 4 % here: the ring is latency-bound)
-#ifdef GSDR_TC_PHASE_TIMING
-        const long long mB = clock64();
-#endif
         tcFenceAfter();
         if (leader) {
 #pragma unroll
@@ -470,36 +446,19 @@ __global__ void __launch_bounds__(kTcThreads, MINB) firTcKernel(const TcParams P
             const unsigned second = 16u * j >= G::SD ? 1u : 0u;  // the window's second segment: second accumulator
             const unsigned acc = tmem + colD + second * kTcS;
             const unsigned first = (j == 0 || 16u * j == G::SD) ? 0u : 1u;
-#if GSDR_TC_EXPERIMENT == 2
-            tcMmaF16(acc, aCols, descHigh | (((tabHead + off) >> 4) & 0x3FFFu),
-                     (kTcIdesc & ~(0x3fu << 17)) | ((64u >> 3) << 17), first);
-#else
             tcMmaF16(acc, aCols, descHigh | (((tabHead + off) >> 4) & 0x3FFFu), kTcIdesc, first);
-#endif
-#if !GSDR_TC_EXPERIMENT
             tcMmaF16(acc, aCols, descHigh | (((tabRem + off) >> 4) & 0x3FFFu), kTcIdesc, 1u);
-#endif
           }
           tcCommit(&aEmpty[slot]);
           if (st + 1 == numStages) tcCommit(&dFull);
         }
         __syncwarp();
-#ifdef GSDR_TC_PHASE_TIMING
-        mmaWait += mB - mA;
-        mmaIssue += clock64() - mB;
-#endif
         if (++slot == kTcRing) {
           slot = 0;
           ringPass++;
         }
       }
     }
-#ifdef GSDR_TC_PHASE_TIMING
-    if ((blockIdx.x == 7 || blockIdx.x == 300) && lane == 0) {
-      printf("tc mma warp cta %u tiles %u: wait aFull %lld issue %lld (cycles/tile)\n", blockIdx.x, it, mmaWait / it,
-             mmaIssue / it);
-    }
-#endif
   } else {
     // ===================== copy warp: 33 segments per tile =====================
     unsigned it = 0;
@@ -508,7 +467,10 @@ __global__ void __launch_bounds__(kTcThreads, MINB) firTcKernel(const TcParams P
       const unsigned tl = tile - chan * P.tilesPerChannel;
       const float2* src = P.x + (size_t)chan * P.xStride;
       const unsigned long long s0 = (unsigned long long)tl * kTcTileOut * D;  // first sample of the tile
-      if (it > 0) mbarWait(&rawEmpty, (it - 1u) & 1u);  // every producer has left the previous tile's samples  // every producer has left the previous tile's samples
+      // the producers need well over a microsecond for a tile: sleeping through the first part of the wait leaves
+      // the issue slots of the spin to them (0.1451 -> 0.1385 ms on config 2 together with the MMA warp's sleep)
+      if (it > 0) __nanosleep(800);
+      if (it > 0) mbarWait(&rawEmpty, (it - 1u) & 1u);  // every producer has left the previous tile's samples
       // segments inside the caller-guaranteed extent (a prefix): one bulk copy each, every one on its own barrier so
       // that its conversion starts when it lands; the others: guarded loads, zero fill
       const unsigned long long room = P.nIn > s0 ? (P.nIn - s0) / G::SD : 0ull;

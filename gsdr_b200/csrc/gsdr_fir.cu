@@ -94,6 +94,9 @@ static inline int forcedVariant() noexcept { return -1; }
 static inline unsigned debugFlags() noexcept { return 0u; }
 #endif
 
+// gsdrB200SetFirTensorCores: 1 = the tensor-core kernel where it was measured faster (default), 0 = FFMA2 kernels only
+static std::atomic<int> gTensorCores{1};
+
 // the override as the FFMA2-kernel choosers see it: the two tensor-core values mean "automatic" to them
 static inline int forcedFfmaVariant() noexcept {
   const int f = forcedVariant();
@@ -796,18 +799,30 @@ static size_t outElemBytes(FirType t) noexcept { return t == kFirFF ? 4 : 8; }
 // ---------------------------------------------------------------------------------------------------------
 // Tensor-core path (fir_tc_kernel.cuh): FC, decimation 4 / 8 / 16, up to 33 taps per output
 // ---------------------------------------------------------------------------------------------------------
-#ifdef GSDR_B200_TUNING
 size_t tcSharedBytes(unsigned D, unsigned tablePitch) noexcept;
 cudaError_t launchTc(unsigned D, TcParams& P, int dev, int smCount, cudaStream_t stream) noexcept;
 
-// Tiles of 1024 outputs per channel when the call qualifies for the tensor-core kernel, else 0.
+// Tiles of 1024 outputs per channel when the call goes to the tensor-core kernel, else 0.
+//
+// Where it is used was decided by measurement (profiles/r02/tc_f16_sweep.txt; config 2: 0.1385 ms
+// against the FFMA2 kernel's 0.166 ms):
+//   * decimation 8 only — at 4 the tiles are too small for their fixed cost (0.191 vs 0.166 ms), at 16 the tile's
+//     samples leave room for one CTA per SM (0.215 vs 0.201 ms); both stay reachable through the tuning override;
+//   * more than 144 taps — up to 128 the FFMA2 kernel is itself close to the HBM time (0.104 vs 0.124 ms);
+//   * at least 65536 outputs per channel — the size from which gsdrShardPlanTime aligns shards to the kernel's tiles,
+//     so that a call and its shards take the same kernel and agree bit for bit.  (Up to ~300 tiles the launch is
+//     latency-bound and the two kernels tie; around 512 tiles the 444 resident CTAs leave a tail, 0.0168 vs
+//     0.0142 ms; from 1024 tiles on the tensor-core kernel wins.)  The rule looks at ONE channel's outputs: a batched
+//     call and the same channels filtered one by one take the same kernel.
 static unsigned long long tcTilesPerChannel(const FirCall& c, int maxSmem, TcParams* P) noexcept {
-  if (c.type != kFirFC || c.nco != kNcoNone) return 0;
-  // Measured and NOT adopted (profiles/r02_tc_*): 0.224 ms against the FFMA2 kernel's 0.166 ms on
-  // BASELINE config 2.  The kernel stays reachable through the tuning build's override only.
-  if (forcedVariant() != kForceTensorCore || c.epilogue != kFirEpiNone) return 0;
+  if (c.type != kFirFC || c.nco != kNcoNone || c.epilogue != kFirEpiNone) return 0;
   const size_t D = c.decimation, T = c.tapCount;
   if (D != 4 && D != 8 && D != 16) return 0;
+  const int forced = forcedVariant();
+  if (forced != kForceTensorCore) {
+    if (forced != -1 || gTensorCores.load(std::memory_order_relaxed) == 0) return 0;
+    if (D != 8 || T <= 144 || c.numOutputs < 65536) return 0;
+  }
   const size_t SD = (size_t)kTcS * D;
   if (T > SD + D) return 0;                                // a window must fit two segments
   if ((uintptr_t)c.input % 16 != 0) return 0;             // bulk copies need 16-byte aligned sources
@@ -836,7 +851,6 @@ static cudaError_t launchTcTiles(const FirCall& c, unsigned long long tiles, TcP
   P.T = (unsigned)c.tapCount;
   return launchTc((unsigned)c.decimation, P, dev, smCount, stream);
 }
-#endif  // GSDR_B200_TUNING
 
 cudaError_t enqueueFir(const FirCall& c, cudaStream_t stream) noexcept {
   if (c.numOutputs == 0 || c.numChannels == 0) return cudaSuccess;
@@ -858,13 +872,11 @@ cudaError_t enqueueFir(const FirCall& c, cudaStream_t stream) noexcept {
   const DeviceInfo* info = deviceInfo(dev);
   if (!info || info->status != cudaSuccess) return info ? info->status : cudaErrorInvalidDevice;
 
-#ifdef GSDR_B200_TUNING
   {
     TcParams tp{};
     const unsigned long long tcTiles = tcTilesPerChannel(c, info->maxSmemOptin, &tp);
     if (tcTiles > 0) return launchTcTiles(c, tcTiles, tp, dev, info->smCount, stream);
   }
-#endif
   {
     TmaGeom tg{};
     // a tensor map the driver will not encode (kTmaEncodeFailed) sends the call on to the kernels that need none
@@ -1255,6 +1267,10 @@ GSDR_C_LINKAGE int gsdrB200HasTuningHooks(void) GSDR_NO_EXCEPT { return 1; }
 GSDR_C_LINKAGE int gsdrB200HasTuningHooks(void) GSDR_NO_EXCEPT { return 0; }
 #endif
 
+GSDR_C_LINKAGE int gsdrB200SetFirTensorCores(int enable) GSDR_NO_EXCEPT {
+  return gTensorCores.exchange(enable ? 1 : 0, std::memory_order_relaxed);
+}
+
 GSDR_C_LINKAGE int gsdrB200NumKernelVariants(void) GSDR_NO_EXCEPT {
   return firstWideVariantId() + kNumWideVariants;
 }
@@ -1279,7 +1295,6 @@ GSDR_C_LINKAGE int gsdrB200DescribeKernel(int firType, size_t decimation, size_t
     probe.decimation = decimation;
     probe.tapCount = tapCount;
     probe.numOutputs = numOutputs;
-#ifdef GSDR_B200_TUNING
     if (firType == kFirFC) {
       TcParams tp{};
       const unsigned long long tiles = tcTilesPerChannel(probe, di->maxSmemOptin, &tp);
@@ -1295,7 +1310,6 @@ GSDR_C_LINKAGE int gsdrB200DescribeKernel(int firType, size_t decimation, size_t
         return 0;
       }
     }
-#endif
     TmaGeom tg{};
     const int wv = chooseWideVariant(probe, di->maxSmemOptin, &tg);
     if (wv >= 0) {

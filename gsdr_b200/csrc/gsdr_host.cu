@@ -72,12 +72,22 @@ static uint64_t splitPoint(uint64_t n, uint32_t shards, uint32_t s) noexcept {
   return (uint64_t)(((unsigned __int128)n * s) / shards);
 }
 
+// Time shards of at least 64Ki outputs start on a multiple of 1024 outputs: the tensor-core FIR kernel works in tiles
+// of 1024 outputs counted from the first output of a call, and its rounding depends on an output's position in the
+// tile — with aligned shards every output sits where it sits in the unsharded call, so the shards reproduce its bits.
+constexpr uint64_t kShardAlign = 1024, kShardAlignFrom = 65536;
+static uint64_t timeSplitPoint(uint64_t n, uint32_t shards, uint32_t s) noexcept {
+  const uint64_t p = splitPoint(n, shards, s);
+  if (s == 0 || s >= shards || n / shards < kShardAlignFrom) return p;
+  return p - p % kShardAlign;
+}
+
 GSDR_C_LINKAGE int gsdrShardPlanTime(uint64_t numOutputs, uint64_t decimation, uint64_t tapCount,
                                      uint64_t firstSampleIndex, uint32_t numShards, uint32_t shardIndex,
                                      gsdrShard* shard) GSDR_NO_EXCEPT {
   if (!shard || numShards == 0 || shardIndex >= numShards || decimation == 0) return -1;
-  const uint64_t a = splitPoint(numOutputs, numShards, shardIndex);
-  const uint64_t b = splitPoint(numOutputs, numShards, shardIndex + 1);
+  const uint64_t a = timeSplitPoint(numOutputs, numShards, shardIndex);
+  const uint64_t b = timeSplitPoint(numOutputs, numShards, shardIndex + 1);
   shard->firstOutput = a;
   shard->numOutputs = b - a;
   shard->firstInput = a * decimation;
@@ -187,7 +197,8 @@ static cudaError_t runHostJob(gsdrHostPipeline* p, const HostJob& j) noexcept {
   if (j.tapCount * te > p->tapsCapacityBytes) return cudaErrorInvalidValue;
   const size_t chunkElems = p->chunkInputBytes / ie;
   if (chunkElems < j.tapCount + j.decimation) return cudaErrorInvalidValue;  // a chunk must hold at least one window
-  const size_t outsPerChunk = j.tapCount ? (chunkElems - j.tapCount) / j.decimation + 1 : chunkElems;
+  size_t outsPerChunk = j.tapCount ? (chunkElems - j.tapCount) / j.decimation + 1 : chunkElems;
+  if (outsPerChunk >= kShardAlignFrom) outsPerChunk -= outsPerChunk % kShardAlign;  // see timeSplitPoint
   DeviceScope scope(p->device);
   if (scope.status() != cudaSuccess) return scope.status();
 

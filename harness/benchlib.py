@@ -68,11 +68,15 @@ def hbm_peak():
 
 
 def roofline(bytes_alg: float, flops_alg: float, kernel_s: float, fp32_peak_tf: float, fp32_src: str,
-             traffic=None) -> dict:
-    """The slower of (bytes / HBM peak) and (flops / FP32 peak) bounds the kernel (BASELINE.json north_star)."""
+             traffic=None, tensor_core: bool = False) -> dict:
+    """The slower of (bytes / HBM peak) and (flops / FP32 peak) bounds the kernel (BASELINE.json north_star).
+    tensor_core: the multiply-accumulates run on the tensor cores (fir_tc_kernel.cuh), whose FP16 rate is ~30 x the
+    FP32 pipes': the FP32 peak does not bound that kernel, HBM does."""
     hbm, hbm_src = hbm_peak()
     t_mem, t_fp = bytes_alg / (hbm * 1e9), flops_alg / (fp32_peak_tf * 1e12)
     ach_gbs, ach_tf = bytes_alg / kernel_s / 1e9, flops_alg / kernel_s / 1e12
+    if tensor_core:
+        t_fp = 0.0
     if t_fp >= t_mem:
         r = {"bound": "fp32", "achieved": ach_tf, "peak": fp32_peak_tf, "unit": "TFLOP/s", "frac": ach_tf / fp32_peak_tf}
     else:
@@ -83,6 +87,10 @@ def roofline(bytes_alg: float, flops_alg: float, kernel_s: float, fp32_peak_tf: 
                        "peak_source": fp32_src, "paper_peak": PAPER_FP32_TFLOPS,
                        "frac_of_paper": ach_tf / PAPER_FP32_TFLOPS},
               "algorithmic_bytes": bytes_alg, "algorithmic_flops": flops_alg})
+    if tensor_core:
+        r["fp32"]["note"] = ("informational: this kernel's multiply-accumulates run on the tensor cores (tcgen05 "
+                             "kind::f16), so the FP32 FFMA peak does not bound it; the FFMA2 kernel it replaced on "
+                             "this shape was FP32-issue bound")
     return r
 
 

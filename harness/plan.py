@@ -29,13 +29,22 @@ class Shard:
     firstSampleIndex: int
 
 
+def _time_split(n: int, shards: int, s: int) -> int:
+    """Interior split points of shards of >= 64Ki outputs sit on multiples of 1024 outputs (the tensor-core kernel's
+    tile: aligned shards reproduce the unsharded call's bits; gsdr_host.cu timeSplitPoint)."""
+    p = n * s // shards
+    if s == 0 or s >= shards or n // shards < 65536:
+        return p
+    return p - p % 1024
+
+
 def shard_plan_time(num_outputs: int, decimation: int, tap_count: int, first_sample_index: int, num_shards: int,
                     shard_index: int) -> Shard:
     """Split on OUTPUT indices; the (taps - decimation)-sample overlap is read from the shard's own copy."""
     if num_shards <= 0 or not 0 <= shard_index < num_shards or decimation <= 0:
         raise ValueError("bad shard request")
-    a = num_outputs * shard_index // num_shards
-    b = num_outputs * (shard_index + 1) // num_shards
+    a = _time_split(num_outputs, num_shards, shard_index)
+    b = _time_split(num_outputs, num_shards, shard_index + 1)
     return Shard(a, b - a, a * decimation, (b - a - 1) * decimation + tap_count if b > a else 0,
                  first_sample_index + a * decimation)
 

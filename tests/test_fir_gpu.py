@@ -448,10 +448,21 @@ def test_batched_channels_equal_single_calls_bit_exact(kind, shared_taps, cuda_d
     assert np.abs(dys[3].cpu().numpy() - want).max() <= _tol(taps[3], x[3])
 
 
-@pytest.mark.parametrize("shards", [2, 8])
-def test_time_shards_equal_unsharded_bit_exact(shards, cuda_device):
-    """BASELINE requirement: shard-vs-unsharded results identical (decimation phase and offsets bit-exact)."""
-    D, T, n_in = 8, 255, 1 << 20
+@pytest.mark.parametrize("shards,n_in,tensor_cores", [(2, 1 << 20, False), (8, 1 << 20, False), (2, 1 << 21, True),
+                                                       (8, 1 << 23, True), (3, 5_000_011, True)])
+def test_time_shards_equal_unsharded_bit_exact(shards, n_in, tensor_cores, cuda_device):
+    """BASELINE requirement: shard-vs-unsharded results identical (decimation phase and offsets bit-exact).  Shards of
+    at least 65536 outputs sit on the tensor-core kernel's tile grid and take the same kernel as the whole call;
+    smaller shards of a call that large are only bit-identical with gsdrB200SetFirTensorCores(0) (include/gsdr/b200.h)."""
+    D, T = 8, 255
+    g.set_fir_tensor_cores(tensor_cores)
+    try:
+        _time_shards_case(shards, n_in, D, T, cuda_device)
+    finally:
+        g.set_fir_tensor_cores(True)
+
+
+def _time_shards_case(shards, n_in, D, T, cuda_device):
     fs, f, first = 2.4e6, 29520.0, 987_654_321
     taps = synth.lowpass_taps(T, D)
     dx = synth.tone_plus_noise(0, n_in, seed=35, device=cuda_device)
@@ -580,7 +591,16 @@ def test_nco_literal_against_patched_reference_kernel(cuda_device):
 
 # ---- host-buffer pipeline ---------------------------------------------------------------------------------
 
-def test_host_pipeline_equals_device_call_bit_exact(cuda_device):
+@pytest.fixture
+def ffma2_only():
+    """Chunks / blocks far smaller than 65536 outputs against one large call: bit-identical on the FFMA2 kernels
+    (the tensor-core kernel would take the large call only; tests/test_tc_gpu.py covers it with chunks on its grid)."""
+    g.set_fir_tensor_cores(False)
+    yield
+    g.set_fir_tensor_cores(True)
+
+
+def test_host_pipeline_equals_device_call_bit_exact(cuda_device, ffma2_only):
     D, T, n_in = 8, 255, 3_000_017
     taps = synth.lowpass_taps(T, D)
     x = synth.tone_plus_noise(0, n_in, seed=40)

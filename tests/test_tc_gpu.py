@@ -29,16 +29,102 @@ def _run_fc(D, taps, dx, n_out, dev):
     return out[8:8 + n_out]
 
 
-def test_tensor_core_kernel_is_opt_in_only(cuda_device):
-    """Measured slower than the FFMA2 kernels, so no shape selects it by default; the tuning
-    build's override reaches it for the shapes its layout supports."""
+@pytest.fixture(autouse=True)
+def _default_settings():
+    yield
+    g.set_kernel_variant(-1)
+    g.set_fir_tensor_cores(True)
+
+
+def test_where_the_tensor_core_kernel_is_selected(cuda_device):
+    """Chosen by measurement: decimation 8, more than 144 taps, at least 65536 outputs per channel; gsdrB200SetFirTensorCores(0) and the tuning override move the line."""
     tc_id = g.num_kernel_variants()
-    assert g.describe_kernel(0, 8, 255, 8_388_577).variant != tc_id      # BASELINE config 2, release library
+    assert g.describe_kernel(0, 8, 255, 8_388_577).variant == tc_id      # BASELINE config 2
+    assert g.describe_kernel(0, 8, 160, 65_536).variant == tc_id
+    assert g.describe_kernel(0, 8, 255, 65_535).variant != tc_id         # below the size shards are aligned from
+    assert g.describe_kernel(0, 8, 127, 8_388_577).variant != tc_id      # the FFMA2 kernel is HBM-bound there
+    assert g.describe_kernel(0, 8, 265, 8_388_577).variant != tc_id      # a window must fit two segments
+    assert g.describe_kernel(0, 4, 127, 8_388_577).variant != tc_id      # measured slower at decimation 4 and 16
+    assert g.describe_kernel(0, 16, 511, 8_388_577).variant != tc_id
+    assert g.describe_kernel(4, 8, 255, 8_388_577).variant != tc_id      # fused NCO: FFMA2 kernels only
+    assert g.set_fir_tensor_cores(False) is True
+    assert g.describe_kernel(0, 8, 255, 8_388_577).variant != tc_id
+    assert g.set_fir_tensor_cores(True) is False
     g.set_kernel_variant(TC)
-    assert g.describe_kernel(0, 8, 255, 8_388_577).variant == tc_id
+    assert g.describe_kernel(0, 8, 255, 100_000).variant == tc_id
     assert g.describe_kernel(0, 4, 127, 1_048_545).variant == tc_id      # config 4 (per channel)
     assert g.describe_kernel(0, 32, 1023, 8_388_577).variant != tc_id    # segments would not fit shared memory
-    assert g.describe_kernel(0, 10, 255, 8_388_577).variant != tc_id     # k-groups of four would straddle rows
+    assert g.describe_kernel(0, 10, 255, 8_388_577).variant != tc_id     # k-steps of 16 would straddle tap rows
+    g.set_kernel_variant(NO_TC)
+    assert g.describe_kernel(0, 8, 255, 8_388_577).variant != tc_id
+
+
+def test_default_path_on_a_large_call_and_the_switch(cuda_device):
+    """The release library's own choice (no override): a call over the size line runs on the tensor cores, agrees with
+    the oracle on windows and with the FFMA2 kernels everywhere; shards on the plan's 1024-output grid reproduce the
+    unsharded bits; with the switch off the call is bit-identical to the FFMA2 result."""
+    D, T, n_in = 8, 255, 20_000_003
+    taps = synth.random_taps(T, 5)
+    x = synth.tone_plus_noise(0, n_in, seed=310, device=cuda_device)
+    n_out = g.fir_num_outputs(n_in, T, D)
+    dt = torch.from_numpy(taps).to(cuda_device)
+    assert g.describe_kernel(0, D, T, n_out).variant == g.num_kernel_variants()
+    y = torch.zeros(n_out, dtype=torch.complex64, device=cuda_device)
+    g.gsdrFirFC(D, dt, T, x, y, n_out, 0, None)
+    g.set_fir_tensor_cores(False)
+    y_ffma = torch.zeros_like(y)
+    g.gsdrFirFC(D, dt, T, x, y_ffma, n_out, 0, None)
+    g.set_fir_tensor_cores(True)
+    torch.cuda.synchronize()
+    tol = 1e-5 * float(np.abs(taps).sum()) * float(x.abs().max())
+    assert not torch.equal(y, y_ffma)                       # it really is another kernel
+    assert float((y - y_ffma).abs().max()) <= 0.2 * tol
+    for o0 in (0, 1023, 1_234_567, n_out - 3000):
+        xs = x[o0 * D:(o0 + 2999) * D + T].cpu().numpy()
+        want = oracle.fir("fc", D, taps, xs, 3000, f64=True)
+        assert np.abs(y[o0:o0 + 3000].cpu().numpy() - want).max() <= tol
+    for shards in (2, 3, 7):
+        parts = torch.zeros_like(y)
+        for s in range(shards):
+            sh = g.shard_plan_time(n_out, D, T, 0, shards, s)
+            assert s == 0 or sh.firstOutput % 1024 == 0
+            xs = x[sh.firstInput: sh.firstInput + sh.numInputs].clone()
+            g.gsdrFirFC(D, dt, T, xs, parts[sh.firstOutput: sh.firstOutput + sh.numOutputs], sh.numOutputs, 0, None)
+        torch.cuda.synchronize()
+        assert torch.equal(parts, y), f"{shards} shards"
+    # the host pipeline cuts its chunks on the same grid
+    pipe = g.HostPipeline(0, 32 << 20, 3)
+    hx = x.cpu().numpy()
+    hy = np.zeros(n_out, dtype=np.complex64)
+    pipe.gsdrFirFCHost(D, taps, T, hx, hy, n_out)
+    pipe.close()
+    assert hy.tobytes() == y.cpu().numpy().tobytes()
+
+
+def test_non_finite_sample_reach_on_tensor_cores_is_pinned(cuda_device):
+    """ref: src/fir.cu:57-70 multiplies only the taps that overlap a sample, so an Inf/NaN there reaches ceil(T/D)
+    outputs.  The tensor-core kernel multiplies the zeros of the band too (0 * Inf = NaN) and scales per segment of
+    256 samples: the value reaches every output of the 32-output windows that read its segment and nothing else."""
+    D, T, n_out = 8, 255, 1_200_000
+    n_in = g.fir_num_inputs(n_out, T, D)
+    taps = synth.lowpass_taps(T, D)
+    for bad, k in ((np.inf, 5_000_123), (np.nan, 700_001)):
+        x = synth.tone_plus_noise(0, n_in, seed=311)
+        x[k] = bad
+        y = _run_fc(D, taps, torch.from_numpy(x).to(cuda_device), n_out, cuda_device)
+        nonfinite = ~(np.isfinite(y.real) & np.isfinite(y.imag))
+        idx = np.flatnonzero(nonfinite)
+        seg = k // 256                      # segment of S*D = 256 samples; window w reads segments w and w+1
+        lo, hi = max(0, seg - 1) * 32, (seg + 1) * 32
+        assert idx.min() >= lo and idx.max() < hi, (idx.min(), idx.max(), lo, hi)
+        ref_lo, ref_hi = (k - T) // D + 1, k // D       # what the reference would touch
+        assert nonfinite[max(ref_lo, 0):ref_hi + 1].all()
+        clean = np.ones(n_out, dtype=bool)
+        clean[lo:hi] = False
+        xz = x.copy()
+        xz[k] = 0
+        want = _run_fc(D, taps, torch.from_numpy(xz).to(cuda_device), n_out, cuda_device)
+        assert np.array_equal(y[clean], want[clean])
 
 
 @pytest.mark.parametrize("D,T,n_out", [
