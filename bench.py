@@ -473,8 +473,9 @@ def strong_scaling(c: Ctx, steps: int, warmup: int) -> dict:
     mine = e0.elapsed_time(e1) / steps
     ms = c.max_ranks(mine)
     parity = bl.check_fir_windows("fc", D, taps, x0, y, sh.numOutputs)
+    info = g.describe_kernel(0, D, T, sh.numOutputs, c.local)
     roof = bl.roofline(8 * sh.numInputs + 8 * sh.numOutputs + 4 * T, 4.0 * T * sh.numOutputs, mine * 1e-3, c.fp32_peak,
-                       c.fp32_src)
+                       c.fp32_src, tensor_core=info.variant == g.num_kernel_variants())
     # the 67 MB of outputs of this capture collected on rank 0 (NCCL send/recv into the final buffer)
     counts = [g.shard_plan_time(n_out_total, D, T, 0, c.world, r).numOutputs for r in range(c.world)]
     firsts = [g.shard_plan_time(n_out_total, D, T, 0, c.world, r).firstOutput for r in range(c.world)]
@@ -492,7 +493,8 @@ def strong_scaling(c: Ctx, steps: int, warmup: int) -> dict:
             "input_samples_total": n_in_total, "per_rank_us": [v * 1e3 for v in c.all_ranks(mine)],
             "launch": f"one CUDA graph of {steps} gsdrFirFC launches per rank",
             "l2": f"{copies} rotating input copies of {sh.numInputs * 8 >> 20} MiB per rank (> 2x the 126 MB L2 together)",
-            "roofline": roof, "parity": parity, "clocks": sampler.summary(), "gpu_launches": steps}
+            "roofline": roof, "parity": parity, "clocks": sampler.summary(), "gpu_launches": steps,
+            "kernel": _kernel_text(g, info)}
 
 
 def gather_block(c: Ctx, st: dict, steps: int) -> dict:
