@@ -254,3 +254,51 @@ def test_unaligned_input_falls_back_and_still_matches(cuda_device):
     y = _run_fc(D, taps, dx, n_out, cuda_device)
     want = oracle.fir("fc", D, taps, x[1:], n_out, f64=True)
     assert np.abs(y - want).max() <= _tol(taps, x)
+
+
+def test_tensor_core_kernel_is_deterministic_run_to_run(cuda_device):
+    """Persistent CTAs, mbarrier hand-overs between three kinds of warps, in-place conversion of the staged samples: a
+    missing ordering would show up as run-to-run differences.  40 launches of a ragged shape, identical bits."""
+    D, T, n_out = 8, 255, 700_001
+    n_in = g.fir_num_inputs(n_out, T, D)
+    taps = torch.from_numpy(synth.random_taps(T, 21)).to(cuda_device)
+    x = synth.tone_plus_noise(0, n_in, seed=320, device=cuda_device)
+    g.set_kernel_variant(TC)
+    first = torch.zeros(n_out, dtype=torch.complex64, device=cuda_device)
+    g.gsdrFirFC(D, taps, T, x, first, n_out, 0, None)
+    for _ in range(40):
+        y = torch.full((n_out,), float("nan"), dtype=torch.complex64, device=cuda_device)
+        g.gsdrFirFC(D, taps, T, x, y, n_out, 0, None)
+        torch.cuda.synchronize()
+        assert torch.equal(y, first)
+
+
+def test_tensor_core_random_shapes_against_the_ffma2_kernels(cuda_device):
+    """Random (decimation, taps, outputs, channels): the two kernel families agree within a fifth of the oracle
+    tolerance everywhere, and nothing is written outside the outputs.  GSDR_TC_FUZZ_CASES widens it."""
+    import os
+
+    rng = np.random.default_rng(int(os.environ.get("GSDR_TC_FUZZ_SEED", "7")))
+    for case in range(int(os.environ.get("GSDR_TC_FUZZ_CASES", "24"))):
+        D = int(rng.choice([4, 8, 8, 8, 16]))
+        T = int(rng.integers(1, 33 * D + 1))
+        n_out = int(rng.integers(1, 200_000))
+        C = int(rng.choice([1, 1, 1, 3]))
+        n_in = g.fir_num_inputs(n_out, T, D)
+        n_in += n_in & 1            # even channel stride: the batched bulk-copy path needs 16-byte aligned channels
+        taps = synth.random_taps(T, 1000 + case)
+        xs = synth.tone_plus_noise(0, C * n_in, seed=2000 + case, device=cuda_device).view(C, n_in)
+        dt = torch.from_numpy(taps).to(cuda_device)
+        outs = {}
+        for name, v in (("tc", TC), ("ffma2", NO_TC)):
+            g.set_kernel_variant(v)
+            if name == "tc":
+                assert g.describe_kernel(0, D, T, n_out).variant == g.num_kernel_variants(), (D, T, n_out)
+            y = torch.full((C, n_out + 9), float("nan"), dtype=torch.complex64, device=cuda_device)
+            g.gsdrFirFCBatched(D, dt, T, 0, xs, n_in, y, n_out + 9, n_out, C, 0, None)
+            torch.cuda.synchronize()
+            assert bool(torch.isnan(y[:, n_out:].real).all()), f"case {case}: wrote past the outputs"
+            outs[name] = y[:, :n_out]
+        tol = 1e-5 * float(np.abs(taps).sum()) * float(xs.abs().max())
+        err = float((outs["tc"] - outs["ffma2"]).abs().max())
+        assert err <= 0.2 * tol + 1e-30, f"case {case}: D={D} T={T} n_out={n_out} C={C}: {err} > {0.2 * tol}"
