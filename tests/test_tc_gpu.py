@@ -302,3 +302,39 @@ def test_tensor_core_random_shapes_against_the_ffma2_kernels(cuda_device):
         tol = 1e-5 * float(np.abs(taps).sum()) * float(xs.abs().max())
         err = float((outs["tc"] - outs["ffma2"]).abs().max())
         assert err <= 0.2 * tol + 1e-30, f"case {case}: D={D} T={T} n_out={n_out} C={C}: {err} > {0.2 * tol}"
+
+
+def test_tensor_core_call_in_a_cuda_graph_and_on_two_streams(cuda_device):
+    """include/gsdr/fir.h: work is enqueued on cudaStream only and can be captured into a CUDA graph.  Two streams
+    running the kernel at the same time share the SM's tensor memory (every CTA allocates 128 of its 512 columns and
+    waits for them if another kernel's CTAs hold them): same bits as the calls run one after the other."""
+    D, T, n_out = 8, 255, 300_000
+    n_in = g.fir_num_inputs(n_out, T, D)
+    taps = torch.from_numpy(synth.random_taps(T, 31)).to(cuda_device)
+    xs = [synth.tone_plus_noise(0, n_in, seed=330 + i, device=cuda_device) for i in range(2)]
+    want = [torch.zeros(n_out, dtype=torch.complex64, device=cuda_device) for _ in range(2)]
+    for i in range(2):
+        g.gsdrFirFC(D, taps, T, xs[i], want[i], n_out, 0, None)
+    torch.cuda.synchronize()
+    assert g.describe_kernel(0, D, T, n_out).variant == g.num_kernel_variants()   # the release library's own choice
+    # two streams at once, several rounds
+    streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+    got = [torch.zeros_like(w) for w in want]
+    for _ in range(10):
+        for i in range(2):
+            g.gsdrFirFC(D, taps, T, xs[i], got[i], n_out, 0, streams[i])
+    for s in streams:
+        s.synchronize()
+    assert torch.equal(got[0], want[0]) and torch.equal(got[1], want[1])
+    # captured into a graph and replayed
+    out = torch.zeros_like(want[0])
+    cap = torch.cuda.Stream()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.stream(cap):
+        with torch.cuda.graph(graph, stream=cap):
+            g.gsdrFirFC(D, taps, T, xs[0], out, n_out, 0, cap)
+            g.gsdrFirFC(D, taps, T, xs[0], out, n_out, 0, cap)
+    out.zero_()
+    graph.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(out, want[0])
