@@ -422,10 +422,18 @@ __global__ void __launch_bounds__(kTcThreads, MINB) firTcKernel(const TcParams P
     }
   } else if (warp == kMmaWarp) {
     // ===================== MMA issue =====================
+    // This warp shares its scheduler with seven others, so every instruction between a stage becoming ready and its
+    // MMAs being issued is latency on the ring: descriptors, TMEM addresses and barrier addresses advance by constant
+    // steps instead of being recomputed (the k-step's tap rows move down by 16/D table entries per step).
     const unsigned leader = tcElectOne();
-    const unsigned tabHead = smemU32(tables), tabRem = tabHead + 2u * P.tablePitch;
     const unsigned long long descHigh =
         ((unsigned long long)((128u >> 4) | (1u << 14)) << 32) | ((unsigned long long)((P.tablePitch >> 4) & 0x3FFFu) << 16);
+    const unsigned long long descHead0 = descHigh | (unsigned long long)((smemU32(tables) + 16u * P.aMax) >> 4);
+    const unsigned remDelta = (2u * P.tablePitch) >> 4;  // head table -> remainder table, in 16-byte units
+    constexpr unsigned kStepDelta = 16u / D;             // table entries (= 16-byte units) per k-step
+    constexpr unsigned kSecondFrom = G::SD / 32u;        // first stage of the window's second segment
+    const unsigned aFullAddr = tcKeep(smemU32(&aFull[0])), aEmptyAddr = tcKeep(smemU32(&aEmpty[0]));
+    const unsigned ring0 = tcKeep(tmem + 2u * kTcS);
     unsigned slot = 0, ringPass = 0, it = 0;
     for (unsigned tile = blockIdx.x; tile < P.totalTiles; tile += gridDim.x, it++) {
       if (it > 0) {
@@ -433,25 +441,24 @@ __global__ void __launch_bounds__(kTcThreads, MINB) firTcKernel(const TcParams P
         mbarWait(&dEmpty, (it - 1u) & 1u);  // the epilogue has read the previous tile's accumulators
         tcFenceAfter();
       }
+      unsigned long long bHead = descHead0;
       for (unsigned st = 0; st < numStages; st++) {
-        mbarWait(&aFull[slot], ringPass & 1u);  // (a suspended wait costs 4 % here: the ring is latency-bound)
+        tcBarWait(aFullAddr + 8u * slot, ringPass & 1u);  // (a suspended wait costs 4 % here)
         tcFenceAfter();
         if (leader) {
-#pragma unroll
-          for (unsigned half = 0; half < 2; half++) {
-            const unsigned j = 2u * st + half;  // k-step: k = 16j .. 16j+15
-            const unsigned a = (16u * j) / D;   // tap-row offset of the step's first sample
-            const unsigned off = 16u * (P.aMax - a);
-            const unsigned aCols = slotCols(slot) + 8u * half;
-            const unsigned second = 16u * j >= G::SD ? 1u : 0u;  // the window's second segment: second accumulator
-            const unsigned acc = tmem + colD + second * kTcS;
-            const unsigned first = (j == 0 || 16u * j == G::SD) ? 0u : 1u;
-            tcMmaF16(acc, aCols, descHigh | (((tabHead + off) >> 4) & 0x3FFFu), kTcIdesc, first);
-            tcMmaF16(acc, aCols, descHigh | (((tabRem + off) >> 4) & 0x3FFFu), kTcIdesc, 1u);
-          }
-          tcCommit(&aEmpty[slot]);
+          const unsigned acc = tmem + colD + (st >= kSecondFrom ? (unsigned)kTcS : 0u);
+          const unsigned first = (st == 0u || st == kSecondFrom) ? 0u : 1u;
+          const unsigned aCols = ring0 + 16u * slot;
+          tcMmaF16(acc, aCols, bHead, kTcIdesc, first);
+          tcMmaF16(acc, aCols, bHead + remDelta, kTcIdesc, 1u);
+          tcMmaF16(acc, aCols + 8u, bHead - kStepDelta, kTcIdesc, 1u);
+          tcMmaF16(acc, aCols + 8u, bHead - kStepDelta + remDelta, kTcIdesc, 1u);
+          asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
+                           aEmptyAddr + 8u * slot)
+                       : "memory");
           if (st + 1 == numStages) tcCommit(&dFull);
         }
+        bHead -= 2u * kStepDelta;
         __syncwarp();
         if (++slot == kTcRing) {
           slot = 0;
