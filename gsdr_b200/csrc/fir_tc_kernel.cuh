@@ -180,6 +180,11 @@ __device__ __forceinline__ void tcBarWait(unsigned barAddr, unsigned parity) {
       "r"(parity)
       : "memory");
 }
+__device__ __forceinline__ uint4 tcLoadShared16(unsigned addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  return v;
+}
 __device__ __forceinline__ void tcBarArrive(unsigned barAddr) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(barAddr) : "memory");
 }
@@ -270,7 +275,8 @@ __global__ void __launch_bounds__(kTcThreads, MINB) firTcKernel(const TcParams P
     const unsigned laneAddr = tcKeep((32u * quad) << 16);
     const unsigned aFullAddr = tcKeep(smemU32(&aFull[0])), aEmptyAddr = tcKeep(smemU32(&aEmpty[0]));
     const unsigned ringBase = tcKeep(tmem + 2u * kTcS + laneAddr);
-    const unsigned char* row = raw + q * G::segPitch + (2u * comp + part) * G::planeBytes;
+    const unsigned rowAddr = tcKeep(smemU32(raw + q * G::segPitch + (2u * comp + part) * G::planeBytes));
+    const unsigned numStagesK = tcKeep(numStages);
     const unsigned lastSegValid = P.T > (unsigned)D ? P.T - (unsigned)D : 0u;  // (S-1)*D + T - S*D
     unsigned g = 0;                 // stage counter over all tiles of this CTA: stage g belongs to warpgroup g & 1
     unsigned it = 0;
@@ -327,29 +333,29 @@ __global__ void __launch_bounds__(kTcThreads, MINB) firTcKernel(const TcParams P
       // ---- stages: 32 samples of this row's plane -> 16 TMEM columns; the warpgroups take alternate stages ----
       // a warp's own stages are st0, st0 + 2, ...; the loads of its next stage are in flight while the tcgen05.st of
       // the current one completes
-      auto stageSrc = [&](unsigned st) {
+      auto stageSrc = [&](unsigned st) {  // shared-memory address of the row's 64 bytes of stage st
         const unsigned k = 32u * st;
         const unsigned over = k >= G::SD ? 1u : 0u;  // second segment of the window (stages never straddle)
-        return reinterpret_cast<const uint4*>(row + over * G::segPitch + (k - over * G::SD) * 2u);
+        return rowAddr + over * G::segPitch + (k - over * G::SD) * 2u;
       };
       const unsigned st0 = (g ^ group) & 1u;
       unsigned slot = (g + st0) % kTcRing, ringPass = (g + st0) / kTcRing;
       uint4 av[4];
-      if (st0 < numStages) {
-        const uint4* src = stageSrc(st0);
+      if (st0 < numStagesK) {
+        const unsigned src = stageSrc(st0);
 #pragma unroll
-        for (int j = 0; j < 4; j++) av[j] = src[j];
+        for (int j = 0; j < 4; j++) av[j] = tcLoadShared16(src + 16u * j);
       }
-      for (unsigned st = st0; st < numStages; st += 2) {
+      for (unsigned st = st0; st < numStagesK; st += 2) {
         if (ringPass > 0) {
           tcBarWait(aEmptyAddr + 8u * slot, (ringPass - 1u) & 1u);  // the MMAs that read this slot have completed
           tcFenceAfter();
         }
         tcStore16(ringBase + 16u * slot, av);
-        if (st + 2 < numStages) {
-          const uint4* src = stageSrc(st + 2);
+        if (st + 2 < numStagesK) {
+          const unsigned src = stageSrc(st + 2);
 #pragma unroll
-          for (int j = 0; j < 4; j++) av[j] = src[j];
+          for (int j = 0; j < 4; j++) av[j] = tcLoadShared16(src + 16u * j);
         }
         asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
         tcFenceBefore();
