@@ -11,7 +11,7 @@
 // Precision: FP16 operands, error-compensated.  tools/tc_probe.cu / tc_probe_f16.cu measured what the hardware gives:
 // a kind::tf32 MMA (K = 8) costs 26 + 0.46 N cycles whatever the accumulator pattern — 40.5 at N = 32 — while
 // kind::f16 (K = 16) runs at N/2 + 2 (17.3 at N = 32): per multiply-accumulate FP16 is ~5 x cheaper, which pays for
-// splitting.  Samples and taps are scaled by powers of two into [0.5, 1) (per tile / per call) and split,
+// splitting.  Samples and taps are scaled by powers of two into [0.5, 1) (per segment and component / per call) and split,
 //     x*sx = xh + xl,   h*sh = hh + hl,   xh = top 11 significant bits (exact in FP16), xl = FP16(x*sx - xh),
 // and ALL FOUR partial products reach the FP32 accumulators (rows of both sample parts, two MMAs per k-step for the
 // two tap parts; the epilogue adds the head row and the remainder row), so nothing is dropped; what remains is the
@@ -199,7 +199,7 @@ __global__ void __launch_bounds__(kTcThreads, MINB) firTcKernel(const TcParams P
   using G = TcGeom<D>;
   extern __shared__ __align__(16) unsigned char smemRaw[];
   __shared__ __align__(8) unsigned long long segFull[G::numSegs], rawEmpty, dFull, dEmpty, aFull[kTcRing], aEmpty[kTcRing];
-  __shared__ int segExp[G::numSegs];  // per segment: the exponent its samples were scaled by
+  __shared__ int segExp[2][G::numSegs];  // per component (re, im) and segment: the exponent it was scaled by
   __shared__ unsigned tmemBaseSlot;
   __shared__ unsigned redMax[kTcThreads / 32];
   unsigned char* raw = smemRaw;                  // numSegs x segPitch
@@ -304,20 +304,26 @@ __global__ void __launch_bounds__(kTcThreads, MINB) firTcKernel(const TcParams P
             if (i0 + 1u >= lastSegValid) c[p].z = c[p].w = 0.0f;
           }
         }
-        float mf = 0.0f;
+        // re and im are separate rows of the GEMM, so each gets its own scale: a component much smaller than the other
+        // keeps its own relative precision (and an Inf in one does not reach the other)
+        float mRe = 0.0f, mIm = 0.0f;
 #pragma unroll
         for (int p = 0; p < kPasses; p++) {
-          mf = fmaxf(fmaxf(mf, fabsf(c[p].x)), fmaxf(fmaxf(fabsf(c[p].y), fabsf(c[p].z)), fabsf(c[p].w)));
+          mRe = fmaxf(mRe, fmaxf(fabsf(c[p].x), fabsf(c[p].z)));
+          mIm = fmaxf(mIm, fmaxf(fabsf(c[p].y), fabsf(c[p].w)));
         }
-        // (the reduction also orders every lane's loads before the stores below)
-        const unsigned m = __reduce_max_sync(0xffffffffu, __float_as_uint(mf));
-        const int xExp = tcScaleExponent(m);
-        const float sx = tcPow2(xExp);
-        if (lane == 0) segExp[sg] = xExp;
+        // (the reductions also order every lane's loads before the stores below)
+        const int reExp = tcScaleExponent(__reduce_max_sync(0xffffffffu, __float_as_uint(mRe)));
+        const int imExp = tcScaleExponent(__reduce_max_sync(0xffffffffu, __float_as_uint(mIm)));
+        const float sRe = tcPow2(reExp), sIm = tcPow2(imExp);
+        if (lane == 0) {
+          segExp[0][sg] = reExp;
+          segExp[1][sg] = imExp;
+        }
 #pragma unroll
         for (int p = 0; p < kPasses; p++) {
-          const float a = c[p].x * sx, b = c[p].z * sx;  // re of samples 2i, 2i+1
-          const float e = c[p].y * sx, f = c[p].w * sx;  // im
+          const float a = c[p].x * sRe, b = c[p].z * sRe;  // re of samples 2i, 2i+1
+          const float e = c[p].y * sIm, f = c[p].w * sIm;  // im
           const float ah = __uint_as_float(__float_as_uint(a) & kTcHeadMask);
           const float bh = __uint_as_float(__float_as_uint(b) & kTcHeadMask);
           const float eh = __uint_as_float(__float_as_uint(e) & kTcHeadMask);
@@ -368,7 +374,7 @@ __global__ void __launch_bounds__(kTcThreads, MINB) firTcKernel(const TcParams P
       }
       g += numStages;
       // (read before the arrive: the next tile's conversion rewrites segExp as soon as its copies have landed)
-      const int e1 = -(segExp[q] + tapExp), e2 = -(segExp[q + 1] + tapExp);
+      const int e1 = -(segExp[comp][q] + tapExp), e2 = -(segExp[comp][q + 1] + tapExp);
       mbarArrive(&rawEmpty);  // this thread has no more reads of the tile's samples
       // ---- epilogue: head row + remainder row -> y, undoing both scales (exact powers of two, in two factors to
       //      stay in range); warpgroup 0 takes the accumulator's columns 0..15, warpgroup 1 columns 16..31 ----

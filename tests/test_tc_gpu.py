@@ -338,3 +338,21 @@ def test_tensor_core_call_in_a_cuda_graph_and_on_two_streams(cuda_device):
     graph.replay()
     torch.cuda.synchronize()
     assert torch.equal(out, want[0])
+
+
+def test_tensor_core_components_keep_their_own_precision(cuda_device):
+    """re and im are scaled separately: an imaginary part seven orders of magnitude below the real part (and the other
+    way round) comes out with the tolerance of ITS OWN level, as on the FP32 pipes."""
+    D, T, n_out = 8, 255, 150_000
+    n_in = g.fir_num_inputs(n_out, T, D)
+    taps = synth.random_taps(T, 41)
+    h1 = float(np.abs(taps).sum())
+    g.set_kernel_variant(TC)
+    for small_im in (True, False):
+        x = synth.tone_plus_noise(0, n_in, seed=340)
+        x = (x.real + 1j * x.imag * np.float32(1e-7)) if small_im else (x.real * np.float32(1e-7) + 1j * x.imag)
+        x = x.astype(np.complex64)
+        y = _run_fc(D, taps, torch.from_numpy(x).to(cuda_device), n_out, cuda_device)
+        want = oracle.fir("fc", D, taps, x, n_out, f64=True)
+        assert np.abs(y.real - want.real).max() <= 1e-5 * h1 * float(np.abs(x.real).max())
+        assert np.abs(y.imag - want.imag).max() <= 1e-5 * h1 * float(np.abs(x.imag).max())
