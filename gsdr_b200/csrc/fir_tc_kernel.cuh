@@ -1,6 +1,7 @@
 // fir_tc_kernel.cuh — decimating FIR, complex input x real taps (gsdrFirFC), on the 5th-generation tensor cores.
-// Replaces ref: src/fir.cu:49-71 (k_FirDecimate<cuComplex,cuComplex,float>) for shapes with many taps per output
-// (BASELINE configs 2 and 4), where the FFMA2 kernel of fir_tma_kernel.cuh is bound by FP32 issue slots.
+// Replaces ref: src/fir.cu:49-71 (k_FirDecimate<cuComplex,cuComplex,float>) where it was measured faster than the
+// FFMA2 kernel of fir_tma_kernel.cuh, which is bound by FP32 issue slots: decimation 8, 145..264 taps (BASELINE
+// config 2).  The selection rule and every measurement behind it: gsdr_fir.cu tcTilesPerChannel, DESIGN.md §4.3b.
 //
 // Formulation (banded Toeplitz GEMM).  A window of S = 32 consecutive outputs starting at output o0 reads the
 // K = (S-1)*D + T consecutive samples starting at sample o0*D:
@@ -11,47 +12,45 @@
 // Precision: FP16 operands, error-compensated.  tools/tc_probe.cu / tc_probe_f16.cu measured what the hardware gives:
 // a kind::tf32 MMA (K = 8) costs 26 + 0.46 N cycles whatever the accumulator pattern — 40.5 at N = 32 — while
 // kind::f16 (K = 16) runs at N/2 + 2 (17.3 at N = 32): per multiply-accumulate FP16 is ~5 x cheaper, which pays for
-// splitting.  Samples and taps are scaled by powers of two into [0.5, 1) (per segment and component / per call) and split,
+// splitting.  Samples (per segment of S*D samples and per component) and taps (per call) are scaled by powers of two
+// into [0.5, 1) and split,
 //     x*sx = xh + xl,   h*sh = hh + hl,   xh = top 11 significant bits (exact in FP16), xl = FP16(x*sx - xh),
 // and ALL FOUR partial products reach the FP32 accumulators (rows of both sample parts, two MMAs per k-step for the
 // two tap parts; the epilogue adds the head row and the remainder row), so nothing is dropped; what remains is the
-// FP16 rounding of the remainders: <= 2^-21 relative to a value near the tile's maximum, 2^-25 of that maximum for
+// FP16 rounding of the remainders: <= 2^-21 relative to a value near the segment's maximum, 2^-25 of that maximum for
 // small values — FP32-grade against BASELINE's tolerance 1e-5 * sum|h| * max|x| (tests/test_tc_gpu.py holds it to the
-// FFMA2 kernel's own error).  The epilogue undoes the two scales exactly.
-//
-// History of the design, all measured on BASELINE config 2 (FFMA2 kernel: 0.166 ms):
-//   v0  TF32 operands, hi/lo split, rows formed from FP32 samples per k-step: 0.2245 ms, bound by the MMAs
-//       (profiles/r02_tc_d8_fir_tensor_core_full.txt).
-//   v1  FP16 operands, S = 16, every row scaling / splitting / packing its own samples per k-step: 0.277 ms, bound by
-//       the 129 instructions per row-step of the producers (each sample is converted by the ~3 windows that overlap
-//       it; profiles/r02/tc_f16_v1_*).
-//   v2  (this file) every sample is converted ONCE per tile, in place, into four FP16 planes; forming a row is then
-//       four 16-byte shared-memory loads and one tcgen05.st.
+// FFMA2 kernel's own error).  A window spans two segments with two scales: two accumulators, combined by the epilogue,
+// which undoes all scales exactly (powers of two).
 //
 // Operands.
-//   The copy warp brings the tile's raw complex samples into shared memory (each byte is fetched from HBM once per
-//     tile, by one bulk copy per segment of S*D samples).  The four producer warps find the tile's largest component,
-//     then rewrite every segment IN PLACE as four planes of S*D FP16 values: [re head | re remainder | im head | im
-//     remainder] (8 bytes per sample either way).
+//   The copy warp brings the tile's raw complex samples into shared memory: each byte is fetched from HBM once per
+//     tile, by one bulk copy per segment, every segment on its own mbarrier.  The eight producer warps rewrite each
+//     segment IN PLACE as it lands (the conversion overlaps the copies still in flight) as four planes of S*D FP16
+//     values: [re head | re remainder | im head | im remainder] (8 bytes per sample either way).
 //   A comes from TENSOR MEMORY: row (= TMEM lane) 32*w + l holds window 8*w + (l & 7), component (l >> 3) & 1, part
 //     l >> 4; per stage of 32 samples it loads 64 contiguous bytes of its plane and writes 16 columns with one
-//     tcgen05.st; a ring of TMEM stages decouples the producers from the MMAs.
+//     tcgen05.st; a ring of four TMEM stages decouples the producers from the MMAs (the two warpgroups take
+//     alternate stages).
 //   B never exists as a matrix: B[k][s] depends on k - s*D only, so per tap part TWO tables are kept in shared
 //     memory, T_tb[u] = (h[(aMax-u)*D + 8*tb + e])_{e<8} for the first and second group of eight k of a k-step; the
 //     K-major, un-swizzled descriptor of a k-step starts 16*(aMax - a) bytes into table 0 (rows s = 0..31 of the
 //     operand are the next 32 entries: 16-byte row pitch, SBO = 128; LBO = table pitch).  A few KB serve every step.
-//   D (128 x 32 FP32) lives in TMEM; the producer warps read it back with tcgen05.ld when the tile's last MMA has
+//   D (2 x 128 x 32 FP32) lives in TMEM; the producer warps read it back with tcgen05.ld when the tile's last MMA has
 //     been committed.
-// A tile is 1024 outputs (32 windows) of one channel; CTAs are persistent over tiles, up to 3-4 per SM (shared memory:
-// 33 segments + 16 bytes of padding each, so the 8 windows a warp reads hit different banks) — while one CTA
-// computes, another's bulk copies are in flight.  Segments that reach past the caller-guaranteed input are staged by
-// the copy warp with guarded loads and zero fill, and the epilogue masks outputs >= numOutputs: every output of a
-// call goes through the same arithmetic whatever its position in a tile.  (Results still depend on the TILE through
-// its scale factor and the k-step alignment, so time shards reproduce the unsharded call within the tolerance, not
-// bit for bit.)
+// A tile is 1024 outputs (32 windows) of one channel; CTAs are persistent over tiles, three per SM (shared memory:
+// 33 segments + 16 bytes of padding each, so the 8 windows a warp reads hit different banks; 128 of the SM's 512 TMEM
+// columns each) — while one CTA computes, another's bulk copies are in flight.  Segments that reach past the
+// caller-guaranteed input are staged by the copy warp with guarded loads and zero fill, and the epilogue masks outputs
+// >= numOutputs.
 //
-// Non-finite samples: a tile that contains an Inf/NaN keeps scale 1; the value reaches all outputs of its window rows
-// (0 * Inf in the band's zeros); the reference would confine it to the outputs whose taps overlap it.
+// What a result depends on: the tile's own samples and the output's position in the tile (k-step alignment, segment
+// scales) — nothing else; the tile's last segment is masked down to the T - D samples its one reader uses, so the
+// next tile's samples never set a scale.  Calls whose first outputs differ by a multiple of 1024 therefore agree bit
+// for bit on the outputs they share: gsdrShardPlanTime and the host pipeline cut shards / chunks on that grid.
+//
+// Non-finite samples: an Inf/NaN keeps its segment's scale (of its component) at 1 and reaches every output of the
+// windows that read the segment (0 * Inf in the band's zeros); the reference confines it to the outputs whose taps
+// overlap it (tests/test_tc_gpu.py pins the reach).
 #pragma once
 
 #include <cuda_fp16.h>
