@@ -217,10 +217,11 @@ class Ctx:
         """W warm-up steps, then K timed steps bracketed by barrier + synchronize; returns (this rank's ms per step,
         max-over-ranks ms per step, clock summary)."""
         t = self.torch
+        sampler = bl.ClockSampler(self.local).start()  # (NVML set-up and thread start cost milliseconds: not here ↓)
         for _ in range(warmup):
             step()
         self.barrier()
-        sampler = bl.ClockSampler(self.local).start()
+        sampler.begin()
         if flush_between:
             total = 0.0
             for _ in range(steps):

@@ -159,6 +159,12 @@ class ClockSampler:
             self._thr.start()
         return self
 
+    def begin(self):
+        """Forget what was sampled so far (warm-up): the summary covers the timed region only.  The thread is started
+        BEFORE the warm-up so that nothing but this call sits between the barrier and the first timed launch."""
+        self.samples, self.power, self.reasons = [], [], set()
+        return self
+
     def stop(self):
         if self._thr is not None:
             try:
