@@ -1,6 +1,6 @@
 // fir_tc_kernel.cuh — decimating FIR, complex input x real taps (gsdrFirFC), on the 5th-generation tensor cores.
 // Replaces ref: src/fir.cu:49-71 (k_FirDecimate<cuComplex,cuComplex,float>) where it was measured faster than the
-// FFMA2 kernel of fir_tma_kernel.cuh, which is bound by FP32 issue slots: decimation 8, 145..264 taps (BASELINE
+// FFMA2 kernel of fir_tma_kernel.cuh, which is bound by FP32 issue slots: decimation 8, 129..264 taps (BASELINE
 // config 2).  The selection rule and every measurement behind it: gsdr_fir.cu tcTilesPerChannel, DESIGN.md §4.3b.
 //
 // Formulation (banded Toeplitz GEMM).  A window of S = 32 consecutive outputs starting at output o0 reads the

@@ -808,7 +808,8 @@ cudaError_t launchTc(unsigned D, TcParams& P, int dev, int smCount, cudaStream_t
 // against the FFMA2 kernel's 0.166 ms):
 //   * decimation 8 only — at 4 the tiles are too small for their fixed cost (0.191 vs 0.166 ms), at 16 the tile's
 //     samples leave room for one CTA per SM (0.215 vs 0.201 ms); both stay reachable through the tuning override;
-//   * more than 144 taps — up to 128 the FFMA2 kernel is itself close to the HBM time (0.104 vs 0.124 ms);
+//   * more than 128 taps — up to 128 the FFMA2 kernel is itself close to the HBM time (0.107 vs 0.133 ms at 127
+//     taps); from 129 on it pays for 160 (0.170 ms against 0.132 ms at 129 taps);
 //   * at least 65536 outputs per channel — the size from which gsdrShardPlanTime aligns shards to the kernel's tiles,
 //     so that a call and its shards take the same kernel and agree bit for bit.  (Up to ~300 tiles the launch is
 //     latency-bound and the two kernels tie; around 512 tiles the 444 resident CTAs leave a tail, 0.0168 vs
@@ -821,7 +822,7 @@ static unsigned long long tcTilesPerChannel(const FirCall& c, int maxSmem, TcPar
   const int forced = forcedVariant();
   if (forced != kForceTensorCore) {
     if (forced != -1 || gTensorCores.load(std::memory_order_relaxed) == 0) return 0;
-    if (D != 8 || T <= 144 || c.numOutputs < 65536) return 0;
+    if (D != 8 || T <= 128 || c.numOutputs < 65536) return 0;
   }
   const size_t SD = (size_t)kTcS * D;
   if (T > SD + D) return 0;                                // a window must fit two segments

@@ -37,10 +37,12 @@ def _default_settings():
 
 
 def test_where_the_tensor_core_kernel_is_selected(cuda_device):
-    """Chosen by measurement: decimation 8, more than 144 taps, at least 65536 outputs per channel; gsdrB200SetFirTensorCores(0) and the tuning override move the line."""
+    """Chosen by measurement: decimation 8, more than 128 taps, at least 65536 outputs per channel; gsdrB200SetFirTensorCores(0) and the tuning override move the line."""
     tc_id = g.num_kernel_variants()
     assert g.describe_kernel(0, 8, 255, 8_388_577).variant == tc_id      # BASELINE config 2
     assert g.describe_kernel(0, 8, 160, 65_536).variant == tc_id
+    assert g.describe_kernel(0, 8, 129, 65_536).variant == tc_id
+    assert g.describe_kernel(0, 8, 128, 8_388_577).variant != tc_id
     assert g.describe_kernel(0, 8, 255, 65_535).variant != tc_id         # below the size shards are aligned from
     assert g.describe_kernel(0, 8, 127, 8_388_577).variant != tc_id      # the FFMA2 kernel is HBM-bound there
     assert g.describe_kernel(0, 8, 265, 8_388_577).variant != tc_id      # a window must fit two segments
