@@ -31,7 +31,8 @@ static cudaError_t launchTcT(TcParams& P, size_t smem, int dev, int smCount, cud
       const int bySmem = (int)((size_t)smemPerSm / (smem + 1024 + 256));
       if (bySmem > perSm) perSm = bySmem;
     }
-    const int tmemLimit = 512 / (int)kTcTmemCols;  // every CTA owns kTcTmemCols of the SM's 512 TMEM columns
+    // every CTA owns kTcTmemCols (+ the ring's second allocation at 64 outputs per window) of the SM's 512 columns
+    const int tmemLimit = 512 / (int)(kTcTmemCols + tcTmemCols2(tcWindowOutputs(D)));
     if (perSm > tmemLimit) perSm = tmemLimit;
     if (perSm > MINB) perSm = MINB;
     perSmCache[dev & 63].store(perSm, std::memory_order_release);

@@ -3,7 +3,7 @@
 // FFMA2 kernel of fir_tma_kernel.cuh, which is bound by FP32 issue slots: decimation 8, 129..264 taps (BASELINE
 // config 2).  The selection rule and every measurement behind it: gsdr_fir.cu tcTilesPerChannel, DESIGN.md §4.3b.
 //
-// Formulation (banded Toeplitz GEMM).  A window of S = 32 consecutive outputs starting at output o0 reads the
+// Formulation (banded Toeplitz GEMM).  A window of S = 32 (decimation 4: 64) consecutive outputs starting at output o0 reads the
 // K = (S-1)*D + T consecutive samples starting at sample o0*D:
 //     y[o0 + s] = sum_k x[o0*D + k] * h[k - s*D]                 (h = 0 outside [0, T))
 // i.e. D[row][s] = sum_k A[row][k] * B[k][s] with one ROW per (window, component, part): re and im are two real
@@ -72,12 +72,14 @@ struct TcParams {
   unsigned tablePitch;  // bytes between the two tables of a tap part: (aMax + S) * 16
 };
 
-constexpr int kTcS = 32;          // outputs per window = MMA N
 constexpr int kTcWindows = 32;    // windows per tile
-constexpr int kTcTileOut = kTcS * kTcWindows;
+// outputs per window = MMA N: 32, or 64 for decimation 4 (a segment of S*D = 256 samples either way)
+__host__ __device__ constexpr int tcWindowOutputs(int D) { return D == 4 ? 64 : 32; }
 // TMEM stages of 16 columns, next to the two accumulators of 32.  (Two more stages in a second allocation of 32
 // columns were measured: 3 % slower — the ring is not what the stage loop waits for.)
-constexpr int kTcRing = 4;
+// (S = 64: two accumulators of 64 columns fill the first allocation; two stages live in a second one of 32 columns)
+__host__ __device__ constexpr int tcRing(int S) { return S == 64 ? 2 : 4; }
+__host__ __device__ constexpr unsigned tcTmemCols2(int S) { return S == 64 ? 32u : 0u; }
 constexpr int kTcProducers = 256;  // warps 0-7: two warpgroups of producers + epilogue (warp w and w + 4 share the
                                    // TMEM lanes 32 * (w & 3) ..: the groups take alternate stages)
 constexpr int kTcThreads = kTcProducers + 64;  // warp 8: MMA issue, warp 9: bulk copies
@@ -86,7 +88,10 @@ constexpr unsigned kTcTmemCols = 128;
 template <int D>
 struct TcGeom {
   static_assert(D == 4 || D == 8 || D == 16, "k-steps of 16 samples must start on a tap row");
-  static constexpr unsigned SD = kTcS * D;             // samples per segment = window stride
+  static constexpr int S = tcWindowOutputs(D);
+  static constexpr int tileOut = S * kTcWindows;
+  static constexpr int ring = tcRing(S);
+  static constexpr unsigned SD = S * D;                // samples per segment = window stride
   static constexpr unsigned segBytes = SD * 8;         // raw: SD complex FP32; converted: four planes of SD FP16
   static constexpr unsigned planeBytes = SD * 2;
   static constexpr unsigned segPitch = segBytes + 16;  // 16 bytes of padding: consecutive windows, different banks
@@ -146,7 +151,9 @@ __device__ __forceinline__ void tcLoad16(unsigned taddr, unsigned (&v)[16]) {
 
 // kind::f16 with FP16 A and B (format 0), FP32 accumulate, A and B K-major, M = 128, N = 32
 // (bit layout: cute/arch/mma_sm100_desc.hpp)
-constexpr unsigned kTcIdesc = (1u << 4) | (0u << 7) | (0u << 10) | ((unsigned)(kTcS >> 3) << 17) | ((128u >> 4) << 24);
+__host__ __device__ constexpr unsigned tcIdesc(int S) {
+  return (1u << 4) | (0u << 7) | (0u << 10) | ((unsigned)(S >> 3) << 17) | ((128u >> 4) << 24);
+}
 constexpr unsigned kTcHeadMask = 0xFFFFE000u;  // sign, exponent, 10 mantissa bits: an FP16 value when in range
 
 // exponent n of the power of two 2^n that brings a value with |bits| `absBits` into [0.5, 1); 0 for Inf and NaN
@@ -196,10 +203,12 @@ __device__ __forceinline__ unsigned tcPackHalf2(float lo, float hi) {
 template <int D, int MINB>
 __global__ void __launch_bounds__(kTcThreads, MINB) firTcKernel(const TcParams P) {
   using G = TcGeom<D>;
+  constexpr int S = G::S, kTcRing = G::ring;
+  constexpr unsigned kTcIdesc = tcIdesc(S);
   extern __shared__ __align__(16) unsigned char smemRaw[];
   __shared__ __align__(8) unsigned long long segFull[G::numSegs], rawEmpty, dFull, dEmpty, aFull[kTcRing], aEmpty[kTcRing];
   __shared__ int segExp[2][G::numSegs];  // per component (re, im) and segment: the exponent it was scaled by
-  __shared__ unsigned tmemBaseSlot;
+  __shared__ unsigned tmemBaseSlot, tmemBaseSlot2;
   __shared__ unsigned redMax[kTcThreads / 32];
   unsigned char* raw = smemRaw;                  // numSegs x segPitch
   unsigned char* tables = smemRaw + G::rawBytes;  // [head | remainder][2][aMax + S] x 16 bytes (8 FP16 taps)
@@ -221,6 +230,11 @@ __global__ void __launch_bounds__(kTcThreads, MINB) firTcKernel(const TcParams P
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smemU32(&tmemBaseSlot)),
                  "r"(kTcTmemCols)
                  : "memory");
+    if (tcTmemCols2(S) > 0) {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smemU32(&tmemBaseSlot2)),
+                   "r"(tcTmemCols2(S))
+                   : "memory");
+    }
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   // tap scale: the largest |h| into [0.5, 1)
@@ -256,7 +270,7 @@ __global__ void __launch_bounds__(kTcThreads, MINB) firTcKernel(const TcParams P
   __syncthreads();
   tcFenceAfter();
   const unsigned tmem = tmemBaseSlot;
-  auto slotCols = [&](unsigned slot) { return tmem + 2u * kTcS + 16u * slot; };
+  const unsigned ringCols = tcTmemCols2(S) > 0 ? tmemBaseSlot2 : tmem + 2u * S;  // first column of the A ring
   // two accumulators of 32 columns (a window's samples in its first / second segment: the segments have their own
   // scales); A ring: kTcRing x 16 columns
   const unsigned colD = 0;
@@ -273,7 +287,7 @@ __global__ void __launch_bounds__(kTcThreads, MINB) firTcKernel(const TcParams P
     const unsigned q = 8u * quad + (lane & 7u);          // window of the tile
     const unsigned laneAddr = tcKeep((32u * quad) << 16);
     const unsigned aFullAddr = tcKeep(smemU32(&aFull[0])), aEmptyAddr = tcKeep(smemU32(&aEmpty[0]));
-    const unsigned ringBase = tcKeep(tmem + 2u * kTcS + laneAddr);
+    const unsigned ringBase = tcKeep(ringCols + laneAddr);
     const unsigned rowAddr = tcKeep(smemU32(raw + q * G::segPitch + (2u * comp + part) * G::planeBytes));
     const unsigned numStagesK = tcKeep(numStages);
     const unsigned lastSegValid = P.T > (unsigned)D ? P.T - (unsigned)D : 0u;  // (S-1)*D + T - S*D
@@ -286,7 +300,7 @@ __global__ void __launch_bounds__(kTcThreads, MINB) firTcKernel(const TcParams P
       // lane holds chunk 32*p + lane of every pass p before the first plane word is written
       for (unsigned sg = warp; sg < G::numSegs; sg += kMmaWarp) {
         unsigned char* seg = raw + sg * G::segPitch;
-        constexpr int kPasses = D / 2;  // SD / 64
+        constexpr int kPasses = G::SD / 64;
         float4 c[kPasses];
         mbarWait(&segFull[sg], it & 1u);
         // the largest |component| (fmaxf drops NaNs: a NaN stays a NaN under any scale; an Inf gives scale 1)
@@ -381,53 +395,60 @@ __global__ void __launch_bounds__(kTcThreads, MINB) firTcKernel(const TcParams P
       tcFenceAfter();
       // v[i] = D1[i] / scale(first segment) + D2[i] / scale(second segment), the tap scale undone in the same factors
       const float f1a = tcPow2(e1 / 2), f1b = tcPow2(e1 - e1 / 2), f2a = tcPow2(e2 / 2), f2b = tcPow2(e2 - e2 / 2);
-      unsigned d[16];
-      float v[16];
-      tcLoad16(tmem + laneAddr + colD + 16u * group, d);
-      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-      for (int i = 0; i < 16; i++) v[i] = (__uint_as_float(d[i]) * f1a) * f1b;
-      if (useSecond) {
-        tcLoad16(tmem + laneAddr + colD + kTcS + 16u * group, d);
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-        for (int i = 0; i < 16; i++) v[i] = fmaf(__uint_as_float(d[i]) * f2a, f2b, v[i]);
-      }
-      tcFenceBefore();
-      mbarArrive(&dEmpty);  // the accumulators may be overwritten by the next tile
-      // the four lanes of a window each end up with four complete outputs: 16*group + 8*part + 4*comp + (0..3).
-      // 1) the two parts trade the half of their columns the other one sums
-      float sum[8];
-#pragma unroll
-      for (int i = 0; i < 8; i++) {
-        const float give = part ? v[i] : v[8 + i];
-        const float keep = part ? v[8 + i] : v[i];
-        sum[i] = keep + __shfl_xor_sync(0xffffffffu, give, 16);
-      }
-      // 2) the two components trade the half of those outputs the other one stores
-      float2 out[4];
-#pragma unroll
-      for (int i = 0; i < 4; i++) {
-        const float give = comp ? sum[i] : sum[4 + i];
-        const float keep = comp ? sum[4 + i] : sum[i];
-        const float got = __shfl_xor_sync(0xffffffffu, give, 8);
-        out[i] = comp ? make_float2(got, keep) : make_float2(keep, got);
-      }
       const unsigned chan = tile / P.tilesPerChannel;
       const unsigned tl = tile - chan * P.tilesPerChannel;
-      const unsigned long long o0 =
-          (unsigned long long)tl * kTcTileOut + q * kTcS + 16u * group + 8u * part + 4u * comp;
-      float2* y = P.y + (size_t)chan * P.yStride + o0;
-      const unsigned valid = o0 >= P.nOut ? 0u : (P.nOut - o0 >= 4ull ? 4u : (unsigned)(P.nOut - o0));
-      if (valid == 4u && (reinterpret_cast<uintptr_t>(y) & 15u) == 0) {
+      // every warpgroup takes half of the accumulators' columns, 16 at a time
 #pragma unroll
-        for (int i = 0; i < 2; i++) {
-          reinterpret_cast<float4*>(y)[i] = make_float4(out[2 * i].x, out[2 * i].y, out[2 * i + 1].x, out[2 * i + 1].y);
+      for (int cp = 0; cp < S / 32; cp++) {
+        const unsigned col0 = (unsigned)(S / 2) * group + 16u * cp;  // first of this pass's 16 outputs of the window
+        unsigned d[16];
+        float v[16];
+        tcLoad16(tmem + laneAddr + colD + col0, d);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+        for (int i = 0; i < 16; i++) v[i] = (__uint_as_float(d[i]) * f1a) * f1b;
+        if (useSecond) {
+          tcLoad16(tmem + laneAddr + colD + S + col0, d);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+          for (int i = 0; i < 16; i++) v[i] = fmaf(__uint_as_float(d[i]) * f2a, f2b, v[i]);
         }
-      } else {
+        if (cp == S / 32 - 1) {
+          tcFenceBefore();
+          mbarArrive(&dEmpty);  // the accumulators may be overwritten by the next tile
+        }
+        // the four lanes of a window each end up with four complete outputs: col0 + 8*part + 4*comp + (0..3).
+        // 1) the two parts trade the half of their columns the other one sums
+        float sum[8];
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+          const float give = part ? v[i] : v[8 + i];
+          const float keep = part ? v[8 + i] : v[i];
+          sum[i] = keep + __shfl_xor_sync(0xffffffffu, give, 16);
+        }
+        // 2) the two components trade the half of those outputs the other one stores
+        float2 out[4];
 #pragma unroll
         for (int i = 0; i < 4; i++) {
-          if ((unsigned)i < valid) y[i] = out[i];
+          const float give = comp ? sum[i] : sum[4 + i];
+          const float keep = comp ? sum[4 + i] : sum[i];
+          const float got = __shfl_xor_sync(0xffffffffu, give, 8);
+          out[i] = comp ? make_float2(got, keep) : make_float2(keep, got);
+        }
+        const unsigned long long o0 = (unsigned long long)tl * G::tileOut + q * S + col0 + 8u * part + 4u * comp;
+        float2* y = P.y + (size_t)chan * P.yStride + o0;
+        const unsigned valid = o0 >= P.nOut ? 0u : (P.nOut - o0 >= 4ull ? 4u : (unsigned)(P.nOut - o0));
+        if (valid == 4u && (reinterpret_cast<uintptr_t>(y) & 15u) == 0) {
+#pragma unroll
+          for (int i = 0; i < 2; i++) {
+            reinterpret_cast<float4*>(y)[i] =
+                make_float4(out[2 * i].x, out[2 * i].y, out[2 * i + 1].x, out[2 * i + 1].y);
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 4; i++) {
+            if ((unsigned)i < valid) y[i] = out[i];
+          }
         }
       }
     }
@@ -444,7 +465,7 @@ __global__ void __launch_bounds__(kTcThreads, MINB) firTcKernel(const TcParams P
     constexpr unsigned kStepDelta = 16u / D;             // table entries (= 16-byte units) per k-step
     constexpr unsigned kSecondFrom = G::SD / 32u;        // first stage of the window's second segment
     const unsigned aFullAddr = tcKeep(smemU32(&aFull[0])), aEmptyAddr = tcKeep(smemU32(&aEmpty[0]));
-    const unsigned ring0 = tcKeep(tmem + 2u * kTcS);
+    const unsigned ring0 = tcKeep(ringCols);
     unsigned slot = 0, ringPass = 0, it = 0;
     for (unsigned tile = blockIdx.x; tile < P.totalTiles; tile += gridDim.x, it++) {
       if (it > 0) {
@@ -457,7 +478,7 @@ __global__ void __launch_bounds__(kTcThreads, MINB) firTcKernel(const TcParams P
         tcBarWait(aFullAddr + 8u * slot, ringPass & 1u);  // (a suspended wait costs 4 % here)
         tcFenceAfter();
         if (leader) {
-          const unsigned acc = tmem + colD + (st >= kSecondFrom ? (unsigned)kTcS : 0u);
+          const unsigned acc = tmem + colD + (st >= kSecondFrom ? (unsigned)S : 0u);
           const unsigned first = (st == 0u || st == kSecondFrom) ? 0u : 1u;
           const unsigned aCols = ring0 + 16u * slot;
           tcMmaF16(acc, aCols, bHead, kTcIdesc, first);
@@ -484,7 +505,7 @@ __global__ void __launch_bounds__(kTcThreads, MINB) firTcKernel(const TcParams P
       const unsigned chan = tile / P.tilesPerChannel;
       const unsigned tl = tile - chan * P.tilesPerChannel;
       const float2* src = P.x + (size_t)chan * P.xStride;
-      const unsigned long long s0 = (unsigned long long)tl * kTcTileOut * D;  // first sample of the tile
+      const unsigned long long s0 = (unsigned long long)tl * G::tileOut * D;  // first sample of the tile
       // the producers need well over a microsecond for a tile: sleeping through the first part of the wait leaves
       // the issue slots of the spin to them (0.1451 -> 0.1385 ms on config 2 together with the MMA warp's sleep)
       if (it > 0) __nanosleep(800);
@@ -518,6 +539,10 @@ __global__ void __launch_bounds__(kTcThreads, MINB) firTcKernel(const TcParams P
   __syncthreads();
   if (warp == kMmaWarp) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(kTcTmemCols) : "memory");
+    if (tcTmemCols2(S) > 0) {
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmemBaseSlot2), "r"(tcTmemCols2(S))
+                   : "memory");
+    }
   }
 }
 

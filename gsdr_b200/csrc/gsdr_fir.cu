@@ -806,7 +806,7 @@ cudaError_t launchTc(unsigned D, TcParams& P, int dev, int smCount, cudaStream_t
 //
 // Where it is used was decided by measurement (profiles/r02/tc_f16_sweep.txt; config 2: 0.1385 ms
 // against the FFMA2 kernel's 0.166 ms):
-//   * decimation 8 only — at 4 the tiles are too small for their fixed cost (0.191 vs 0.166 ms), at 16 the tile's
+//   * decimation 8 only — at 4 twice the outputs per input sample cost too much (0.174 vs 0.1665 ms), at 16 the tile's
 //     samples leave room for one CTA per SM (0.215 vs 0.201 ms); both stay reachable through the tuning override;
 //   * more than 128 taps — up to 128 the FFMA2 kernel is itself close to the HBM time (0.107 vs 0.133 ms at 127
 //     taps); from 129 on it pays for 160 (0.170 ms against 0.132 ms at 129 taps);
@@ -824,16 +824,17 @@ static unsigned long long tcTilesPerChannel(const FirCall& c, int maxSmem, TcPar
     if (forced != -1 || gTensorCores.load(std::memory_order_relaxed) == 0) return 0;
     if (D != 8 || T <= 128 || c.numOutputs < 65536) return 0;
   }
-  const size_t SD = (size_t)kTcS * D;
+  const unsigned S = (unsigned)tcWindowOutputs((int)D), tileOut = S * kTcWindows;
+  const size_t SD = (size_t)S * D;
   if (T > SD + D) return 0;                                // a window must fit two segments
   if ((uintptr_t)c.input % 16 != 0) return 0;             // bulk copies need 16-byte aligned sources
   if (c.numChannels > 1 && (c.tapStride != 0 || (c.inputStride % 2) != 0)) return 0;
-  const unsigned long long tiles = (c.numOutputs + kTcTileOut - 1) / kTcTileOut;
+  const unsigned long long tiles = (c.numOutputs + tileOut - 1) / tileOut;
   if (tiles * c.numChannels > 0x7fffffffull) return 0;
-  const unsigned K = (unsigned)((kTcS - 1) * D + T);
+  const unsigned K = (unsigned)((S - 1) * D + T);
   P->numStages = (K + 31u) / 32u;
   P->aMax = (16u * (2u * P->numStages - 1u)) / (unsigned)D;
-  P->tablePitch = (P->aMax + kTcS) * 16u;
+  P->tablePitch = (P->aMax + S) * 16u;
   if (tcSharedBytes((unsigned)D, P->tablePitch) > (size_t)maxSmem) return 0;
   return tiles;
 }
@@ -1305,7 +1306,7 @@ GSDR_C_LINKAGE int gsdrB200DescribeKernel(int firType, size_t decimation, size_t
         info->threadsPerBlock = kTcThreads;
         info->phaseGroups = 1;
         info->windowBuffers = 1;
-        info->outputsPerBlock = kTcTileOut;
+        info->outputsPerBlock = (size_t)tcWindowOutputs((int)decimation) * kTcWindows;
         info->sharedBytesPerBlock = tcSharedBytes((unsigned)decimation, tp.tablePitch);
         info->numBlocks = (size_t)tiles;
         return 0;
