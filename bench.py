@@ -394,8 +394,9 @@ def case_cfg4(c: Ctx, steps: int, warmup: int) -> dict:
             worst = p
         worst["ok"] = worst["ok"] and p["ok"]
     worst["channels_checked"] = len({0, cn // 2, cn - 1})
-    roof = bl.roofline(cn * (8 * n_in + 8 * n_out) + 4 * T, 4.0 * T * n_out * cn, mine * 1e-3, c.fp32_peak, c.fp32_src)
     info = g.describe_kernel(0, D, T, n_out, c.local)
+    roof = bl.roofline(cn * (8 * n_in + 8 * n_out) + 4 * T, 4.0 * T * n_out * cn, mine * 1e-3, c.fp32_peak, c.fp32_src,
+                       tensor_core=info.variant == g.num_kernel_variants())
     return {"ms_per_step": ms, "value": n_in * chans_total / (ms * 1e-3) / 1e6, "unit": UNIT, "scaling": "strong",
             "channels_this_rank": cn, "roofline": roof, "parity": worst, "clocks": clocks, "gpu_launches": steps,
             "kernel": _kernel_text(g, info), "config": bl.config_block("cfg4", c.world)}

@@ -51,7 +51,7 @@ size_t tcSharedBytes(unsigned D, unsigned tablePitch) noexcept {
 cudaError_t launchTc(unsigned D, TcParams& P, int dev, int smCount, cudaStream_t stream) noexcept {
   const size_t smem = tcSharedBytes(D, P.tablePitch);
   switch (D) {
-    case 4: return launchTcT<4, 3>(P, smem, dev, smCount, stream);
+    case 4: return launchTcT<4, 2>(P, smem, dev, smCount, stream);
     case 8: return launchTcT<8, 3>(P, smem, dev, smCount, stream);
     case 16: return launchTcT<16, 1>(P, smem, dev, smCount, stream);
     default: return cudaErrorInvalidValue;

@@ -1,7 +1,7 @@
 // fir_tc_kernel.cuh — decimating FIR, complex input x real taps (gsdrFirFC), on the 5th-generation tensor cores.
 // Replaces ref: src/fir.cu:49-71 (k_FirDecimate<cuComplex,cuComplex,float>) where it was measured faster than the
-// FFMA2 kernel of fir_tma_kernel.cuh, which is bound by FP32 issue slots: decimation 8, 129..264 taps (BASELINE
-// config 2).  The selection rule and every measurement behind it: gsdr_fir.cu tcTilesPerChannel, DESIGN.md §4.3b.
+// FFMA2 kernel of fir_tma_kernel.cuh, which is bound by FP32 issue slots: decimation 8 with 129..264 taps (BASELINE
+// config 2) and decimation 4 with 65..260 taps (config 4).  The selection rule and every measurement behind it: gsdr_fir.cu tcTilesPerChannel, DESIGN.md §4.3b.
 //
 // Formulation (banded Toeplitz GEMM).  A window of S = 32 (decimation 4: 64) consecutive outputs starting at output o0 reads the
 // K = (S-1)*D + T consecutive samples starting at sample o0*D:
@@ -37,16 +37,16 @@
 //     operand are the next 32 entries: 16-byte row pitch, SBO = 128; LBO = table pitch).  A few KB serve every step.
 //   D (2 x 128 x 32 FP32) lives in TMEM; the producer warps read it back with tcgen05.ld when the tile's last MMA has
 //     been committed.
-// A tile is 1024 outputs (32 windows) of one channel; CTAs are persistent over tiles, three per SM (shared memory:
-// 33 segments + 16 bytes of padding each, so the 8 windows a warp reads hit different banks; 128 of the SM's 512 TMEM
-// columns each) — while one CTA computes, another's bulk copies are in flight.  Segments that reach past the
+// A tile is 32 windows (1024 outputs; 2048 at decimation 4) of one channel; CTAs are persistent over tiles, three per
+// SM (two at decimation 4, whose CTAs hold 256 TMEM columns; shared memory: 33 segments + 16 bytes of padding each,
+// so the 8 windows a warp reads hit different banks) — while one CTA computes, another's bulk copies are in flight.  Segments that reach past the
 // caller-guaranteed input are staged by the copy warp with guarded loads and zero fill, and the epilogue masks outputs
 // >= numOutputs.
 //
 // What a result depends on: the tile's own samples and the output's position in the tile (k-step alignment, segment
 // scales) — nothing else; the tile's last segment is masked down to the T - D samples its one reader uses, so the
-// next tile's samples never set a scale.  Calls whose first outputs differ by a multiple of 1024 therefore agree bit
-// for bit on the outputs they share: gsdrShardPlanTime and the host pipeline cut shards / chunks on that grid.
+// next tile's samples never set a scale.  Calls whose first outputs differ by a multiple of the tile therefore agree
+// bit for bit on the outputs they share: gsdrShardPlanTime and the host pipeline cut shards / chunks on that grid.
 //
 // Non-finite samples: an Inf/NaN keeps its segment's scale (of its component) at 1 and reaches every output of the
 // windows that read the segment (0 * Inf in the band's zeros); the reference confines it to the outputs whose taps
@@ -75,11 +75,15 @@ struct TcParams {
 constexpr int kTcWindows = 32;    // windows per tile
 // outputs per window = MMA N: 32, or 64 for decimation 4 (a segment of S*D = 256 samples either way)
 __host__ __device__ constexpr int tcWindowOutputs(int D) { return D == 4 ? 64 : 32; }
-// TMEM stages of 16 columns, next to the two accumulators of 32.  (Two more stages in a second allocation of 32
-// columns were measured: 3 % slower — the ring is not what the stage loop waits for.)
-// (S = 64: two accumulators of 64 columns fill the first allocation; two stages live in a second one of 32 columns)
-__host__ __device__ constexpr int tcRing(int S) { return S == 64 ? 2 : 4; }
-__host__ __device__ constexpr unsigned tcTmemCols2(int S) { return S == 64 ? 32u : 0u; }
+// The ring of TMEM stages (16 columns each) between the producers and the MMAs:
+//   S = 32: four stages next to the two accumulators of 32 columns in ONE allocation of 128 columns, three CTAs per
+//           SM.  (Measured alternatives: six stages, two of them in a second allocation of 32 columns: 3 % slower;
+//           eight stages in a second allocation of 128 columns with two CTAs per SM: 5 % slower.)
+//   S = 64: the two accumulators of 64 columns fill the first allocation; eight stages in a second allocation of 128
+//           columns, two CTAs per SM (0.1586 ms at decimation 4, 127 taps — with two stages in a second allocation
+//           of 32 columns and three CTAs per SM: 0.174 ms).
+__host__ __device__ constexpr int tcRing(int S) { return S == 64 ? 8 : 4; }
+__host__ __device__ constexpr unsigned tcTmemCols2(int S) { return S == 64 ? 128u : 0u; }
 constexpr int kTcProducers = 256;  // warps 0-7: two warpgroups of producers + epilogue (warp w and w + 4 share the
                                    // TMEM lanes 32 * (w & 3) ..: the groups take alternate stages)
 constexpr int kTcThreads = kTcProducers + 64;  // warp 8: MMA issue, warp 9: bulk copies
@@ -271,7 +275,7 @@ __global__ void __launch_bounds__(kTcThreads, MINB) firTcKernel(const TcParams P
   tcFenceAfter();
   const unsigned tmem = tmemBaseSlot;
   const unsigned ringCols = tcTmemCols2(S) > 0 ? tmemBaseSlot2 : tmem + 2u * S;  // first column of the A ring
-  // two accumulators of 32 columns (a window's samples in its first / second segment: the segments have their own
+  // two accumulators of S columns (a window's samples in its first / second segment: the segments have their own
   // scales); A ring: kTcRing x 16 columns
   const unsigned colD = 0;
   const bool useSecond = P.numStages * 32u > G::SD;

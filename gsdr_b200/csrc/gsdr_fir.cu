@@ -802,18 +802,20 @@ static size_t outElemBytes(FirType t) noexcept { return t == kFirFF ? 4 : 8; }
 size_t tcSharedBytes(unsigned D, unsigned tablePitch) noexcept;
 cudaError_t launchTc(unsigned D, TcParams& P, int dev, int smCount, cudaStream_t stream) noexcept;
 
-// Tiles of 1024 outputs per channel when the call goes to the tensor-core kernel, else 0.
+// Tiles (32 windows of 32 outputs; of 64 at decimation 4) per channel when the call goes to the tensor-core kernel,
+// else 0.
 //
-// Where it is used was decided by measurement (profiles/r02/tc_f16_sweep.txt; config 2: 0.1385 ms
-// against the FFMA2 kernel's 0.166 ms):
-//   * decimation 8 only — at 4 twice the outputs per input sample cost too much (0.174 vs 0.1665 ms), at 16 the tile's
-//     samples leave room for one CTA per SM (0.215 vs 0.201 ms); both stay reachable through the tuning override;
-//   * more than 128 taps — up to 128 the FFMA2 kernel is itself close to the HBM time (0.107 vs 0.133 ms at 127
-//     taps); from 129 on it pays for 160 (0.170 ms against 0.132 ms at 129 taps);
+// Where it is used was decided by measurement (profiles/r02/tc_f16_sweep.txt, 2^26 samples):
+//   * decimation 8, 129..264 taps: 0.132-0.146 ms against the FFMA2 kernel's 0.170 ms (0.2415 ms at 264 taps); up
+//     to 128 taps the FFMA2 kernel is itself close to the HBM time (0.107 vs 0.133 ms at 127 taps);
+//   * decimation 4, 65..260 taps: 0.152-0.176 ms against 0.170 ms (65..128 taps), 0.239 ms (..192), 0.307 ms (..256),
+//     0.4445 ms (260); up to 64 taps FFMA2 wins (0.142 vs 0.153 ms);
+//   * not at decimation 16, where a tile's samples leave room for one CTA per SM (0.215 vs 0.201 ms at 511 taps) —
+//     reachable through the tuning override only;
 //   * at least 65536 outputs per channel — the size from which gsdrShardPlanTime aligns shards to the kernel's tiles,
 //     so that a call and its shards take the same kernel and agree bit for bit.  (Up to ~300 tiles the launch is
-//     latency-bound and the two kernels tie; around 512 tiles the 444 resident CTAs leave a tail, 0.0168 vs
-//     0.0142 ms; from 1024 tiles on the tensor-core kernel wins.)  The rule looks at ONE channel's outputs: a batched
+//     latency-bound and the two kernels tie; around 512 tiles the 444 resident CTAs leave a tail, 0.0170 vs
+//     0.0154 ms; from 1024 tiles on the tensor-core kernel wins.)  The rule looks at ONE channel's outputs: a batched
 //     call and the same channels filtered one by one take the same kernel.
 static unsigned long long tcTilesPerChannel(const FirCall& c, int maxSmem, TcParams* P) noexcept {
   if (c.type != kFirFC || c.nco != kNcoNone || c.epilogue != kFirEpiNone) return 0;
@@ -822,7 +824,7 @@ static unsigned long long tcTilesPerChannel(const FirCall& c, int maxSmem, TcPar
   const int forced = forcedVariant();
   if (forced != kForceTensorCore) {
     if (forced != -1 || gTensorCores.load(std::memory_order_relaxed) == 0) return 0;
-    if (D != 8 || T <= 128 || c.numOutputs < 65536) return 0;
+    if (!((D == 8 && T > 128) || (D == 4 && T > 64)) || c.numOutputs < 65536) return 0;
   }
   const unsigned S = (unsigned)tcWindowOutputs((int)D), tileOut = S * kTcWindows;
   const size_t SD = (size_t)S * D;

@@ -72,10 +72,11 @@ static uint64_t splitPoint(uint64_t n, uint32_t shards, uint32_t s) noexcept {
   return (uint64_t)(((unsigned __int128)n * s) / shards);
 }
 
-// Time shards of at least 64Ki outputs start on a multiple of 1024 outputs: the tensor-core FIR kernel works in tiles
-// of 1024 outputs counted from the first output of a call, and its rounding depends on an output's position in the
-// tile — with aligned shards every output sits where it sits in the unsharded call, so the shards reproduce its bits.
-constexpr uint64_t kShardAlign = 1024, kShardAlignFrom = 65536;
+// Time shards of at least 64Ki outputs start on a multiple of 2048 outputs: the tensor-core FIR kernel works in tiles
+// of 1024 outputs (2048 at decimation 4) counted from the first output of a call, and its rounding depends on an
+// output's position in the tile — with aligned shards every output sits where it sits in the unsharded call, so the
+// shards reproduce its bits.
+constexpr uint64_t kShardAlign = 2048, kShardAlignFrom = 65536;
 static uint64_t timeSplitPoint(uint64_t n, uint32_t shards, uint32_t s) noexcept {
   const uint64_t p = splitPoint(n, shards, s);
   if (s == 0 || s >= shards || n / shards < kShardAlignFrom) return p;

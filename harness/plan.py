@@ -30,12 +30,12 @@ class Shard:
 
 
 def _time_split(n: int, shards: int, s: int) -> int:
-    """Interior split points of shards of >= 64Ki outputs sit on multiples of 1024 outputs (the tensor-core kernel's
-    tile: aligned shards reproduce the unsharded call's bits; gsdr_host.cu timeSplitPoint)."""
+    """Interior split points of shards of >= 64Ki outputs sit on multiples of 2048 outputs (the tensor-core kernel's
+    largest tile: aligned shards reproduce the unsharded call's bits; gsdr_host.cu timeSplitPoint)."""
     p = n * s // shards
     if s == 0 or s >= shards or n // shards < 65536:
         return p
-    return p - p % 1024
+    return p - p % 2048
 
 
 def shard_plan_time(num_outputs: int, decimation: int, tap_count: int, first_sample_index: int, num_shards: int,

@@ -76,8 +76,8 @@ typedef struct gsdrShard {
 
 /*
  * Time-block sharding of one capture: shard s of numShards owns outputs [p(s), p(s+1)), p(s) = floor(s*N/S) — rounded
- * down to a multiple of 1024 when the shards hold at least 65536 outputs each (the tensor-core FIR kernel computes in
- * tiles of 1024 outputs counted from a call's first output; with aligned shards every output is computed exactly as in
+ * down to a multiple of 2048 when the shards hold at least 65536 outputs each (the tensor-core FIR kernel computes in
+ * tiles of 1024 or 2048 outputs counted from a call's first output; with aligned shards every output is computed exactly as in
  * the unsharded call, so shards stay bit-identical to it whichever kernel runs).  Splitting on OUTPUT indices keeps
  * the decimation phase exact; neighbouring shards overlap by tapCount - decimation input samples (read from each
  * shard's own resident copy — nothing is exchanged at run time).  Returns 0, or -1 on invalid arguments.
@@ -308,10 +308,10 @@ GSDR_C_LINKAGE GSDR_PUBLIC int gsdrB200NumKernelVariants(void) GSDR_NO_EXCEPT;
  * FF); ids from there up to gsdrB200NumKernelVariants() are the TMA-fed kernels. */
 GSDR_C_LINKAGE GSDR_PUBLIC int gsdrB200NumPolyphaseVariants(void) GSDR_NO_EXCEPT;
 /*
- * gsdrFirFC calls with decimation 8, 129..264 taps and at least 65536 outputs per channel (16-byte aligned input) run
- * on the tensor cores: FP16 operands with error compensation (gsdr_b200/csrc/fir_tc_kernel.cuh), FP32-grade results
+ * gsdrFirFC calls with decimation 8 and 129..264 taps, or decimation 4 and 65..260 taps, and at least 65536 outputs per
+ * channel (16-byte aligned input) run on the tensor cores: FP16 operands with error compensation (gsdr_b200/csrc/fir_tc_kernel.cuh), FP32-grade results
  * (the same 1e-5 * sum|h| * max|x| bound, measured error ~1e-6 of it relative to the FFMA2 kernels) — but a different
- * rounding than the FFMA2 kernels', depending on an output's position in its tile of 1024.  enable = 0 keeps every
+ * rounding than the FFMA2 kernels', depending on an output's position in its tile of 1024 (2048 at decimation 4).  enable = 0 keeps every
  * call on the FFMA2 kernels (bit-identical results whatever the call's size, ~17 % slower on those shapes);
  * process-wide, default 1.  Returns the previous setting.
  */

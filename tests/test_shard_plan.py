@@ -33,9 +33,9 @@ def test_time_shards_partition_outputs_exactly():
                             assert sh.numInputs == 0
                         if n_out // S < 65536:
                             assert abs(sh.numOutputs - n_out / S) < 1
-                        else:   # big shards start on the tensor-core kernel's tile grid (1024 outputs)
-                            assert abs(sh.numOutputs - n_out / S) <= 1024
-                            assert sh.firstOutput % 1024 == 0
+                        else:   # big shards start on the tensor-core kernel's tile grid (2048 outputs)
+                            assert abs(sh.numOutputs - n_out / S) <= 2048
+                            assert sh.firstOutput % 2048 == 0
                     assert nxt == n_out
 
 

@@ -37,7 +37,8 @@ def _default_settings():
 
 
 def test_where_the_tensor_core_kernel_is_selected(cuda_device):
-    """Chosen by measurement: decimation 8, more than 128 taps, at least 65536 outputs per channel; gsdrB200SetFirTensorCores(0) and the tuning override move the line."""
+    """Chosen by measurement: decimation 8 with more than 128 taps or decimation 4 with more than 64,
+    at least 65536 outputs per channel; gsdrB200SetFirTensorCores(0) and the tuning override move the line."""
     tc_id = g.num_kernel_variants()
     assert g.describe_kernel(0, 8, 255, 8_388_577).variant == tc_id      # BASELINE config 2
     assert g.describe_kernel(0, 8, 160, 65_536).variant == tc_id
@@ -46,7 +47,11 @@ def test_where_the_tensor_core_kernel_is_selected(cuda_device):
     assert g.describe_kernel(0, 8, 255, 65_535).variant != tc_id         # below the size shards are aligned from
     assert g.describe_kernel(0, 8, 127, 8_388_577).variant != tc_id      # the FFMA2 kernel is HBM-bound there
     assert g.describe_kernel(0, 8, 265, 8_388_577).variant != tc_id      # a window must fit two segments
-    assert g.describe_kernel(0, 4, 127, 8_388_577).variant != tc_id      # measured slower at decimation 4 and 16
+    assert g.describe_kernel(0, 4, 127, 1_048_545).variant == tc_id      # BASELINE config 4 (per channel)
+    assert g.describe_kernel(0, 4, 65, 65_536).variant == tc_id
+    assert g.describe_kernel(0, 4, 260, 65_536).variant == tc_id
+    assert g.describe_kernel(0, 4, 64, 8_388_577).variant != tc_id       # the FFMA2 kernel wins up to 64 taps
+    assert g.describe_kernel(0, 4, 261, 8_388_577).variant != tc_id
     assert g.describe_kernel(0, 16, 511, 8_388_577).variant != tc_id
     assert g.describe_kernel(4, 8, 255, 8_388_577).variant != tc_id      # fused NCO: FFMA2 kernels only
     assert g.set_fir_tensor_cores(False) is True
@@ -54,18 +59,19 @@ def test_where_the_tensor_core_kernel_is_selected(cuda_device):
     assert g.set_fir_tensor_cores(True) is False
     g.set_kernel_variant(TC)
     assert g.describe_kernel(0, 8, 255, 100_000).variant == tc_id
-    assert g.describe_kernel(0, 4, 127, 1_048_545).variant == tc_id      # config 4 (per channel)
+    assert g.describe_kernel(0, 4, 33, 100_000).variant == tc_id
     assert g.describe_kernel(0, 32, 1023, 8_388_577).variant != tc_id    # segments would not fit shared memory
     assert g.describe_kernel(0, 10, 255, 8_388_577).variant != tc_id     # k-steps of 16 would straddle tap rows
     g.set_kernel_variant(NO_TC)
     assert g.describe_kernel(0, 8, 255, 8_388_577).variant != tc_id
 
 
-def test_default_path_on_a_large_call_and_the_switch(cuda_device):
+@pytest.mark.parametrize("D,T", [(8, 255), (4, 127)])
+def test_default_path_on_a_large_call_and_the_switch(D, T, cuda_device):
     """The release library's own choice (no override): a call over the size line runs on the tensor cores, agrees with
     the oracle on windows and with the FFMA2 kernels everywhere; shards on the plan's 1024-output grid reproduce the
     unsharded bits; with the switch off the call is bit-identical to the FFMA2 result."""
-    D, T, n_in = 8, 255, 20_000_003
+    n_in = 20_000_003
     taps = synth.random_taps(T, 5)
     x = synth.tone_plus_noise(0, n_in, seed=310, device=cuda_device)
     n_out = g.fir_num_outputs(n_in, T, D)
@@ -81,7 +87,7 @@ def test_default_path_on_a_large_call_and_the_switch(cuda_device):
     tol = 1e-5 * float(np.abs(taps).sum()) * float(x.abs().max())
     assert not torch.equal(y, y_ffma)                       # it really is another kernel
     assert float((y - y_ffma).abs().max()) <= 0.2 * tol
-    for o0 in (0, 1023, 1_234_567, n_out - 3000):
+    for o0 in (0, 2047, 1_234_567, n_out - 3000):
         xs = x[o0 * D:(o0 + 2999) * D + T].cpu().numpy()
         want = oracle.fir("fc", D, taps, xs, 3000, f64=True)
         assert np.abs(y[o0:o0 + 3000].cpu().numpy() - want).max() <= tol
@@ -89,7 +95,7 @@ def test_default_path_on_a_large_call_and_the_switch(cuda_device):
         parts = torch.zeros_like(y)
         for s in range(shards):
             sh = g.shard_plan_time(n_out, D, T, 0, shards, s)
-            assert s == 0 or sh.firstOutput % 1024 == 0
+            assert s == 0 or sh.firstOutput % 2048 == 0
             xs = x[sh.firstInput: sh.firstInput + sh.numInputs].clone()
             g.gsdrFirFC(D, dt, T, xs, parts[sh.firstOutput: sh.firstOutput + sh.numOutputs], sh.numOutputs, 0, None)
         torch.cuda.synchronize()
@@ -103,21 +109,24 @@ def test_default_path_on_a_large_call_and_the_switch(cuda_device):
     assert hy.tobytes() == y.cpu().numpy().tobytes()
 
 
-def test_non_finite_sample_reach_on_tensor_cores_is_pinned(cuda_device):
+@pytest.mark.parametrize("D,T", [(8, 255), (4, 127)])
+def test_non_finite_sample_reach_on_tensor_cores_is_pinned(D, T, cuda_device):
     """ref: src/fir.cu:57-70 multiplies only the taps that overlap a sample, so an Inf/NaN there reaches ceil(T/D)
     outputs.  The tensor-core kernel multiplies the zeros of the band too (0 * Inf = NaN) and scales per segment of
-    256 samples: the value reaches every output of the 32-output windows that read its segment and nothing else."""
-    D, T, n_out = 8, 255, 1_200_000
+    256 samples: the value reaches every output of the windows (32 outputs; 64 at decimation 4) that read its segment
+    and nothing else."""
+    n_out = 1_200_000
     n_in = g.fir_num_inputs(n_out, T, D)
     taps = synth.lowpass_taps(T, D)
-    for bad, k in ((np.inf, 5_000_123), (np.nan, 700_001)):
+    for bad, k in ((np.inf, (n_in * 3) // 5 + 123), (np.nan, 700_001)):
         x = synth.tone_plus_noise(0, n_in, seed=311)
         x[k] = bad
         y = _run_fc(D, taps, torch.from_numpy(x).to(cuda_device), n_out, cuda_device)
         nonfinite = ~(np.isfinite(y.real) & np.isfinite(y.imag))
         idx = np.flatnonzero(nonfinite)
+        S = 256 // D                        # outputs per window
         seg = k // 256                      # segment of S*D = 256 samples; window w reads segments w and w+1
-        lo, hi = max(0, seg - 1) * 32, (seg + 1) * 32
+        lo, hi = max(0, seg - 1) * S, (seg + 1) * S
         assert idx.min() >= lo and idx.max() < hi, (idx.min(), idx.max(), lo, hi)
         ref_lo, ref_hi = (k - T) // D + 1, k // D       # what the reference would touch
         assert nonfinite[max(ref_lo, 0):ref_hi + 1].all()
