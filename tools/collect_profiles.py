@@ -14,7 +14,7 @@ OUT, PROF = ROOT / "gpurun_out", ROOT / "profiles"
 
 for name in ("bench_n1_ours_final.json", "bench_n1_reference_final.json"):
     shutil.copy(OUT / name, PROF / "r02" / name)
-shutil.copy(OUT / "tc_f16_sweep.txt", PROF / "r02" / "tc_f16_sweep.txt")
+# (profiles/r02/tc_f16_sweep.txt is tools/tc_sweep.sh's table plus hand-appended runs: not overwritten here)
 shutil.copy(OUT / "tc_sweep.jsonl", PROF / "r02" / "tc_f16_sweep.jsonl")
 shutil.copy(OUT / "r02_bench_launches.csv", PROF / "r02_bench_launches.csv")
 
@@ -58,20 +58,23 @@ print("traffic cfg2", t["cfg2"], "kernel us", d["gpu__time_duration.sum"])
 
 # SASS evidence
 obj = ROOT / "gsdr_b200" / "csrc" / "build" / "fir_inst_tc.o"
-sass = subprocess.run(["cuobjdump", "-sass", "-fun", "_ZN9gsdr_b20011firTcKernelILi8ELi3EEEvNS_8TcParamsE", str(obj)],
-                      capture_output=True, text=True).stdout
-ev = ["# cuobjdump -sass of gsdr_b200::firTcKernel<8, 3> (release build, gsdr_b200/csrc/build/fir_inst_tc.o, sm_100a):",
-      "# the tcgen05 / TMEM / bulk-copy instructions that prove the path (B200_PROFILING.md mnemonics), with counts."]
-for m in ("UTCHMMA", "UTCBAR", "STTM", "LDTM", "UBLKCP", "SYNCS.ARRIVE", "SYNCS.PHASECHK", "UTCATOMSWS",
-          "FENCE.VIEW.ASYNC", "F2FP", "REDUX", "NANOSLEEP", "LDS.128", "FFMA2", "FFMA "):
-    ev.append(f"{m}: {sum(1 for l in sass.splitlines() if m in l)}")
-ev += ["", "# --- the instructions themselves ---"]
-ev += [l.strip()[:150] for l in sass.splitlines() if any(m in l for m in ("UTCHMMA", "UTCBAR", "STTM", "LDTM", "UBLKCP", "UTCATOMSWS"))]
 log = (ROOT / "gsdr_b200" / "csrc" / "build.log").read_text().splitlines()
-for i, l in enumerate(log):
-    if "firTcKernelILi8ELi3" in l and "Compiling" in l:
-        ev += ["", "# ptxas: " + " | ".join(x.strip() for x in log[i + 1:i + 4])]
-        break
+ev = ["# cuobjdump -sass of the tensor-core kernels (release build, gsdr_b200/csrc/build/fir_inst_tc.o, sm_100a):",
+      "# the tcgen05 / TMEM / bulk-copy instructions that prove the path (B200_PROFILING.md mnemonics), with counts."]
+for sym, name in (("_ZN9gsdr_b20011firTcKernelILi8ELi3EEEvNS_8TcParamsE", "firTcKernel<8, 3> (BASELINE config 2)"),
+                  ("_ZN9gsdr_b20011firTcKernelILi4ELi2EEEvNS_8TcParamsE", "firTcKernel<4, 2> (BASELINE config 4)")):
+    sass = subprocess.run(["cuobjdump", "-sass", "-fun", sym, str(obj)], capture_output=True, text=True).stdout
+    ev += ["", f"## gsdr_b200::{name}"]
+    for m in ("UTCHMMA", "UTCBAR", "STTM", "LDTM", "UBLKCP", "SYNCS.ARRIVE", "SYNCS.PHASECHK", "UTCATOMSWS",
+              "FENCE.VIEW.ASYNC", "F2FP", "REDUX", "NANOSLEEP", "LDS.128", "FFMA2", "FFMA "):
+        ev.append(f"{m}: {sum(1 for l in sass.splitlines() if m in l)}")
+    ev += ["# --- the instructions themselves ---"]
+    ev += [l.strip()[:150] for l in sass.splitlines()
+           if any(m in l for m in ("UTCHMMA", "UTCBAR", "STTM", "LDTM", "UBLKCP", "UTCATOMSWS"))]
+    for i, l in enumerate(log):
+        if sym.split("EEEv")[0][-20:] in l and "Compiling" in l:
+            ev += ["# ptxas: " + " | ".join(x.strip() for x in log[i + 1:i + 4])]
+            break
 (PROF / "r02_tc_sass_evidence.txt").write_text("\n".join(ev) + "\n")
 
 r = json.loads((OUT / "bench_n1_ours_final.json").read_text().strip().splitlines()[-1])
