@@ -32,7 +32,7 @@ static cudaError_t launchTcT(TcParams& P, size_t smem, int dev, int smCount, cud
       if (bySmem > perSm) perSm = bySmem;
     }
     // every CTA owns kTcTmemCols (+ the ring's second allocation at 64 outputs per window) of the SM's 512 columns
-    const int tmemLimit = 512 / (int)(kTcTmemCols + tcTmemCols2(tcWindowOutputs(D)));
+    const int tmemLimit = 512 / (int)(kTcTmemCols + tcTmemCols2(D));
     if (perSm > tmemLimit) perSm = tmemLimit;
     if (perSm > MINB) perSm = MINB;
     perSmCache[dev & 63].store(perSm, std::memory_order_release);

@@ -1,7 +1,7 @@
 // fir_tc_kernel.cuh — decimating FIR, complex input x real taps (gsdrFirFC), on the 5th-generation tensor cores.
 // Replaces ref: src/fir.cu:49-71 (k_FirDecimate<cuComplex,cuComplex,float>) where it was measured faster than the
 // FFMA2 kernel of fir_tma_kernel.cuh, which is bound by FP32 issue slots: decimation 8 with 129..264 taps (BASELINE
-// config 2) and decimation 4 with 65..260 taps (config 4).  The selection rule and every measurement behind it: gsdr_fir.cu tcTilesPerChannel, DESIGN.md §4.3b.
+// config 2), decimation 4 with 65..260 taps (config 4) and decimation 16 with 257..528 taps.  The selection rule and every measurement behind it: gsdr_fir.cu tcTilesPerChannel, DESIGN.md §4.3b.
 //
 // Formulation (banded Toeplitz GEMM).  A window of S = 32 (decimation 4: 64) consecutive outputs starting at output o0 reads the
 // K = (S-1)*D + T consecutive samples starting at sample o0*D:
@@ -38,7 +38,7 @@
 //   D (2 x 128 x 32 FP32) lives in TMEM; the producer warps read it back with tcgen05.ld when the tile's last MMA has
 //     been committed.
 // A tile is 32 windows (1024 outputs; 2048 at decimation 4) of one channel; CTAs are persistent over tiles, three per
-// SM (two at decimation 4, whose CTAs hold 256 TMEM columns; shared memory: 33 segments + 16 bytes of padding each,
+// SM (two at decimation 4, whose CTAs hold 256 TMEM columns; one at decimation 16, whose samples fill the shared memory; shared memory: 33 segments + 16 bytes of padding each,
 // so the 8 windows a warp reads hit different banks) — while one CTA computes, another's bulk copies are in flight.  Segments that reach past the
 // caller-guaranteed input are staged by the copy warp with guarded loads and zero fill, and the epilogue masks outputs
 // >= numOutputs.
@@ -76,14 +76,15 @@ constexpr int kTcWindows = 32;    // windows per tile
 // outputs per window = MMA N: 32, or 64 for decimation 4 (a segment of S*D = 256 samples either way)
 __host__ __device__ constexpr int tcWindowOutputs(int D) { return D == 4 ? 64 : 32; }
 // The ring of TMEM stages (16 columns each) between the producers and the MMAs:
-//   S = 32: four stages next to the two accumulators of 32 columns in ONE allocation of 128 columns, three CTAs per
+//   D = 8 (S = 32): four stages next to the two accumulators of 32 columns in ONE allocation of 128 columns, three CTAs per
 //           SM.  (Measured alternatives: six stages, two of them in a second allocation of 32 columns: 3 % slower;
 //           eight stages in a second allocation of 128 columns with two CTAs per SM: 5 % slower.)
-//   S = 64: the two accumulators of 64 columns fill the first allocation; eight stages in a second allocation of 128
+//   D = 4 (S = 64): the two accumulators of 64 columns fill the first allocation; eight stages in a second allocation of 128
 //           columns, two CTAs per SM (0.1586 ms at decimation 4, 127 taps — with two stages in a second allocation
 //           of 32 columns and three CTAs per SM: 0.174 ms).
-__host__ __device__ constexpr int tcRing(int S) { return S == 64 ? 8 : 4; }
-__host__ __device__ constexpr unsigned tcTmemCols2(int S) { return S == 64 ? 128u : 0u; }
+//   D = 16 (one CTA per SM: its samples fill the shared memory): sixteen stages in a second allocation of 256 columns.
+__host__ __device__ constexpr int tcRing(int D) { return D == 4 ? 8 : D == 16 ? 16 : 4; }
+__host__ __device__ constexpr unsigned tcTmemCols2(int D) { return D == 4 ? 128u : D == 16 ? 256u : 0u; }
 constexpr int kTcProducers = 256;  // warps 0-7: two warpgroups of producers + epilogue (warp w and w + 4 share the
                                    // TMEM lanes 32 * (w & 3) ..: the groups take alternate stages)
 constexpr int kTcThreads = kTcProducers + 64;  // warp 8: MMA issue, warp 9: bulk copies
@@ -94,7 +95,7 @@ struct TcGeom {
   static_assert(D == 4 || D == 8 || D == 16, "k-steps of 16 samples must start on a tap row");
   static constexpr int S = tcWindowOutputs(D);
   static constexpr int tileOut = S * kTcWindows;
-  static constexpr int ring = tcRing(S);
+  static constexpr int ring = tcRing(D);
   static constexpr unsigned SD = S * D;                // samples per segment = window stride
   static constexpr unsigned segBytes = SD * 8;         // raw: SD complex FP32; converted: four planes of SD FP16
   static constexpr unsigned planeBytes = SD * 2;
@@ -234,9 +235,9 @@ __global__ void __launch_bounds__(kTcThreads, MINB) firTcKernel(const TcParams P
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smemU32(&tmemBaseSlot)),
                  "r"(kTcTmemCols)
                  : "memory");
-    if (tcTmemCols2(S) > 0) {
+    if (tcTmemCols2(D) > 0) {
       asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smemU32(&tmemBaseSlot2)),
-                   "r"(tcTmemCols2(S))
+                   "r"(tcTmemCols2(D))
                    : "memory");
     }
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -274,7 +275,7 @@ __global__ void __launch_bounds__(kTcThreads, MINB) firTcKernel(const TcParams P
   __syncthreads();
   tcFenceAfter();
   const unsigned tmem = tmemBaseSlot;
-  const unsigned ringCols = tcTmemCols2(S) > 0 ? tmemBaseSlot2 : tmem + 2u * S;  // first column of the A ring
+  const unsigned ringCols = tcTmemCols2(D) > 0 ? tmemBaseSlot2 : tmem + 2u * S;  // first column of the A ring
   // two accumulators of S columns (a window's samples in its first / second segment: the segments have their own
   // scales); A ring: kTcRing x 16 columns
   const unsigned colD = 0;
@@ -543,8 +544,8 @@ __global__ void __launch_bounds__(kTcThreads, MINB) firTcKernel(const TcParams P
   __syncthreads();
   if (warp == kMmaWarp) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(kTcTmemCols) : "memory");
-    if (tcTmemCols2(S) > 0) {
-      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmemBaseSlot2), "r"(tcTmemCols2(S))
+    if (tcTmemCols2(D) > 0) {
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmemBaseSlot2), "r"(tcTmemCols2(D))
                    : "memory");
     }
   }

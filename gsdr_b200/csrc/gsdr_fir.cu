@@ -810,8 +810,9 @@ cudaError_t launchTc(unsigned D, TcParams& P, int dev, int smCount, cudaStream_t
 //     to 128 taps the FFMA2 kernel is itself close to the HBM time (0.107 vs 0.133 ms at 127 taps);
 //   * decimation 4, 65..260 taps: 0.152-0.176 ms against 0.170 ms (65..128 taps), 0.239 ms (..192), 0.307 ms (..256),
 //     0.4445 ms (260); up to 64 taps FFMA2 wins (0.142 vs 0.153 ms);
-//   * not at decimation 16, where a tile's samples leave room for one CTA per SM (0.215 vs 0.201 ms at 511 taps) —
-//     reachable through the tuning override only;
+//   * decimation 16, 257..528 taps: 0.167-0.194 ms against 0.202 ms (0.2806 ms at 528); up to 256 taps FFMA2 wins
+//     (0.129 vs 0.155-0.167 ms).  (A tile's samples leave room for one CTA per SM there; what made it pay is a ring of
+//     sixteen TMEM stages — with four it took 0.215 ms at 511 taps.)
 //   * at least 65536 outputs per channel — the size from which gsdrShardPlanTime aligns shards to the kernel's tiles,
 //     so that a call and its shards take the same kernel and agree bit for bit.  (Up to ~300 tiles the launch is
 //     latency-bound and the two kernels tie; around 512 tiles the 444 resident CTAs leave a tail, 0.0170 vs
@@ -824,7 +825,7 @@ static unsigned long long tcTilesPerChannel(const FirCall& c, int maxSmem, TcPar
   const int forced = forcedVariant();
   if (forced != kForceTensorCore) {
     if (forced != -1 || gTensorCores.load(std::memory_order_relaxed) == 0) return 0;
-    if (!((D == 8 && T > 128) || (D == 4 && T > 64)) || c.numOutputs < 65536) return 0;
+    if (!((D == 8 && T > 128) || (D == 4 && T > 64) || (D == 16 && T > 256)) || c.numOutputs < 65536) return 0;
   }
   const unsigned S = (unsigned)tcWindowOutputs((int)D), tileOut = S * kTcWindows;
   const size_t SD = (size_t)S * D;

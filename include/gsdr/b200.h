@@ -308,8 +308,8 @@ GSDR_C_LINKAGE GSDR_PUBLIC int gsdrB200NumKernelVariants(void) GSDR_NO_EXCEPT;
  * FF); ids from there up to gsdrB200NumKernelVariants() are the TMA-fed kernels. */
 GSDR_C_LINKAGE GSDR_PUBLIC int gsdrB200NumPolyphaseVariants(void) GSDR_NO_EXCEPT;
 /*
- * gsdrFirFC calls with decimation 8 and 129..264 taps, or decimation 4 and 65..260 taps, and at least 65536 outputs per
- * channel (16-byte aligned input) run on the tensor cores: FP16 operands with error compensation (gsdr_b200/csrc/fir_tc_kernel.cuh), FP32-grade results
+ * gsdrFirFC calls with decimation 8 and 129..264 taps, decimation 4 and 65..260 taps or decimation 16 and 257..528
+ * taps, and at least 65536 outputs per channel (16-byte aligned input) run on the tensor cores: FP16 operands with error compensation (gsdr_b200/csrc/fir_tc_kernel.cuh), FP32-grade results
  * (the same 1e-5 * sum|h| * max|x| bound, measured error ~1e-6 of it relative to the FFMA2 kernels) — but a different
  * rounding than the FFMA2 kernels', depending on an output's position in its tile of 1024 (2048 at decimation 4).  enable = 0 keeps every
  * call on the FFMA2 kernels (bit-identical results whatever the call's size, ~17 % slower on those shapes);

@@ -30,11 +30,11 @@
  *  - NEW: the staged kernels pad the tap set with zeros up to a multiple of 8 or 16 taps per polyphase branch, so an
  *    Inf or NaN input sample can reach outputs up to 16 * decimation samples earlier than the reference's window
  *    would (0 * Inf = NaN); finite inputs are unaffected.
- *  - NEW: gsdrFirFC with decimation 8 and 129..264 taps (or decimation 4 and 65..260 taps), >= 65536 outputs and a
+ *  - NEW: gsdrFirFC with decimation 8 and 129..264 taps (or decimation 4 and 65..260, or 16 and 257..528 taps), >= 65536 outputs and a
  *    16-byte aligned input runs on the tensor
  *    cores (FP16 operands with error compensation, FP32 accumulation): the same error bound (measured ~1e-6 of
  *    sum|taps| * max|input|), but an Inf or NaN sample there reaches every output of the up to three windows (32 outputs;
- *    64 at decimation 4) that read its 256-sample segment.  gsdrB200SetFirTensorCores(0) (gsdr/b200.h) keeps every call on the FMA kernels.
+ *    64 at decimation 4) that read its segment of 256 (decimation 16: 512) samples.  gsdrB200SetFirTensorCores(0) (gsdr/b200.h) keeps every call on the FMA kernels.
  */
 #ifndef GSDR_B200_INCLUDE_GSDR_FIR_H_
 #define GSDR_B200_INCLUDE_GSDR_FIR_H_

@@ -37,8 +37,8 @@ def _default_settings():
 
 
 def test_where_the_tensor_core_kernel_is_selected(cuda_device):
-    """Chosen by measurement: decimation 8 with more than 128 taps or decimation 4 with more than 64,
-    at least 65536 outputs per channel; gsdrB200SetFirTensorCores(0) and the tuning override move the line."""
+    """Chosen by measurement: decimation 8 with more than 128 taps, 4 with more than 64 or 16 with more
+    than 256, at least 65536 outputs per channel; gsdrB200SetFirTensorCores(0) and the tuning override move the line."""
     tc_id = g.num_kernel_variants()
     assert g.describe_kernel(0, 8, 255, 8_388_577).variant == tc_id      # BASELINE config 2
     assert g.describe_kernel(0, 8, 160, 65_536).variant == tc_id
@@ -52,7 +52,10 @@ def test_where_the_tensor_core_kernel_is_selected(cuda_device):
     assert g.describe_kernel(0, 4, 260, 65_536).variant == tc_id
     assert g.describe_kernel(0, 4, 64, 8_388_577).variant != tc_id       # the FFMA2 kernel wins up to 64 taps
     assert g.describe_kernel(0, 4, 261, 8_388_577).variant != tc_id
-    assert g.describe_kernel(0, 16, 511, 8_388_577).variant != tc_id
+    assert g.describe_kernel(0, 16, 511, 8_388_577).variant == tc_id
+    assert g.describe_kernel(0, 16, 257, 65_536).variant == tc_id
+    assert g.describe_kernel(0, 16, 256, 8_388_577).variant != tc_id     # the FFMA2 kernel wins up to 256 taps
+    assert g.describe_kernel(0, 16, 529, 8_388_577).variant != tc_id
     assert g.describe_kernel(4, 8, 255, 8_388_577).variant != tc_id      # fused NCO: FFMA2 kernels only
     assert g.set_fir_tensor_cores(False) is True
     assert g.describe_kernel(0, 8, 255, 8_388_577).variant != tc_id
@@ -66,7 +69,7 @@ def test_where_the_tensor_core_kernel_is_selected(cuda_device):
     assert g.describe_kernel(0, 8, 255, 8_388_577).variant != tc_id
 
 
-@pytest.mark.parametrize("D,T", [(8, 255), (4, 127)])
+@pytest.mark.parametrize("D,T", [(8, 255), (4, 127), (16, 511)])
 def test_default_path_on_a_large_call_and_the_switch(D, T, cuda_device):
     """The release library's own choice (no override): a call over the size line runs on the tensor cores, agrees with
     the oracle on windows and with the FFMA2 kernels everywhere; shards on the plan's 1024-output grid reproduce the
@@ -109,7 +112,7 @@ def test_default_path_on_a_large_call_and_the_switch(D, T, cuda_device):
     assert hy.tobytes() == y.cpu().numpy().tobytes()
 
 
-@pytest.mark.parametrize("D,T", [(8, 255), (4, 127)])
+@pytest.mark.parametrize("D,T", [(8, 255), (4, 127), (16, 511)])
 def test_non_finite_sample_reach_on_tensor_cores_is_pinned(D, T, cuda_device):
     """ref: src/fir.cu:57-70 multiplies only the taps that overlap a sample, so an Inf/NaN there reaches ceil(T/D)
     outputs.  The tensor-core kernel multiplies the zeros of the band too (0 * Inf = NaN) and scales per segment of
@@ -124,8 +127,8 @@ def test_non_finite_sample_reach_on_tensor_cores_is_pinned(D, T, cuda_device):
         y = _run_fc(D, taps, torch.from_numpy(x).to(cuda_device), n_out, cuda_device)
         nonfinite = ~(np.isfinite(y.real) & np.isfinite(y.imag))
         idx = np.flatnonzero(nonfinite)
-        S = 256 // D                        # outputs per window
-        seg = k // 256                      # segment of S*D = 256 samples; window w reads segments w and w+1
+        S = 64 if D == 4 else 32            # outputs per window
+        seg = k // (S * D)                  # segment of S*D samples; window w reads segments w and w+1
         lo, hi = max(0, seg - 1) * S, (seg + 1) * S
         assert idx.min() >= lo and idx.max() < hi, (idx.min(), idx.max(), lo, hi)
         ref_lo, ref_hi = (k - T) // D + 1, k // D       # what the reference would touch
